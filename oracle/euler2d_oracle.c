@@ -1,0 +1,1046 @@
+/* TEST INFRASTRUCTURE ONLY — see euler2d_oracle.h.
+ *
+ * Plain-C restatement of the reference's hot path, every function citing the reference
+ * file:line it follows (paths relative to /root/reference).  Evaluation order matters: C and
+ * C++ parse `a - b*c + d*e*f` as ((a - (b*c)) + ((d*e)*f)), and this file keeps the reference's
+ * expressions in the reference's association so that an IEEE-754 double build without FMA
+ * contraction (-ffp-contract=off, like the reference's g++ -O3 build) is bit-identical to it.
+ */
+#include "euler2d_oracle.h"
+
+#include <ctype.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ID E2DO_ID
+#define IP E2DO_IP
+#define IE E2DO_IE
+#define IU E2DO_IU
+#define IV E2DO_IV
+
+/* ===================================================================================== */
+/* .ini reading: config/inih/ini.cpp:65-150 (parser), config/inih/INIReader.cpp:37-100    */
+/* (case-insensitive "section.name" map, last assignment wins), config/ConfigMap.cpp:32-40 */
+/* (getFloat goes through strtof => every real parameter is rounded to float first).      */
+/* ===================================================================================== */
+#define INI_MAX_LINE 200
+#define INI_MAX_SECTION 50
+#define INI_MAX_NAME 50
+
+typedef struct
+{
+  char * key;
+  char * val;
+} kv_t;
+typedef struct
+{
+  kv_t * kv;
+  int    n, cap;
+} cfgmap_t;
+
+static void
+map_set(cfgmap_t * m, const char * section, const char * name, const char * value)
+{
+  size_t ls = strlen(section), ln = strlen(name);
+  char * key = (char *)malloc(ls + ln + 2);
+  memcpy(key, section, ls);
+  key[ls] = '.';
+  memcpy(key + ls + 1, name, ln + 1);
+  for (char * c = key; *c; ++c)
+    *c = (char)tolower((unsigned char)*c); /* INIReader.cpp:93-100 */
+  for (int k = 0; k < m->n; ++k)
+    if (!strcmp(m->kv[k].key, key))
+    {
+      free(m->kv[k].val);
+      m->kv[k].val = strdup(value);
+      free(key);
+      return;
+    }
+  if (m->n == m->cap)
+  {
+    m->cap = m->cap ? 2 * m->cap : 64;
+    m->kv = (kv_t *)realloc(m->kv, sizeof(kv_t) * (size_t)m->cap);
+  }
+  m->kv[m->n].key = key;
+  m->kv[m->n].val = strdup(value);
+  m->n++;
+}
+
+static const char *
+map_get(const cfgmap_t * m, const char * section, const char * name)
+{
+  char key[256];
+  snprintf(key, sizeof key, "%s.%s", section, name);
+  for (char * c = key; *c; ++c)
+    *c = (char)tolower((unsigned char)*c);
+  for (int k = 0; k < m->n; ++k)
+    if (!strcmp(m->kv[k].key, key))
+      return m->kv[k].val;
+  return NULL;
+}
+
+static void
+map_free(cfgmap_t * m)
+{
+  for (int k = 0; k < m->n; ++k)
+  {
+    free(m->kv[k].key);
+    free(m->kv[k].val);
+  }
+  free(m->kv);
+}
+
+static char *
+rstrip(char * s)
+{
+  char * p = s + strlen(s);
+  while (p > s && isspace((unsigned char)*--p))
+    *p = '\0';
+  return s;
+}
+static char *
+lskip(char * s)
+{
+  while (*s && isspace((unsigned char)*s))
+    s++;
+  return s;
+}
+/* ini.cpp:42-52: stop at c, or at ';' that follows a whitespace character */
+static char *
+find_char_or_comment(char * s, char c)
+{
+  int was_ws = 0;
+  while (*s && *s != c && !(was_ws && *s == ';'))
+  {
+    was_ws = isspace((unsigned char)*s);
+    s++;
+  }
+  return s;
+}
+static void
+strncpy0(char * dst, const char * src, size_t size)
+{
+  size_t n = strlen(src);
+  if (n > size - 1)
+    n = size - 1;
+  memcpy(dst, src, n);
+  dst[n] = '\0';
+}
+
+static int
+ini_parse_file(const char * filename, cfgmap_t * m)
+{
+  char   line[INI_MAX_LINE];
+  char   section[INI_MAX_SECTION] = "";
+  char   prev_name[INI_MAX_NAME] = "";
+  FILE * f = fopen(filename, "r");
+  if (!f)
+    return -1;
+  while (fgets(line, sizeof line, f) != NULL) /* ini.cpp:87 */
+  {
+    char * start = lskip(rstrip(line));
+    if (*prev_name && *start && start > line)
+    { /* ini.cpp:93-100: indented line continues (replaces) the previous name's value */
+      map_set(m, section, prev_name, start);
+    }
+    else if (*start == ';' || *start == '#')
+    {
+    }
+    else if (*start == '[')
+    { /* ini.cpp:106-120 */
+      char * end = find_char_or_comment(start + 1, ']');
+      if (*end == ']')
+      {
+        *end = '\0';
+        strncpy0(section, start + 1, sizeof section);
+        *prev_name = '\0';
+      }
+    }
+    else if (*start && *start != ';')
+    { /* ini.cpp:121-144 */
+      char * end = find_char_or_comment(start, '=');
+      if (*end == '=')
+      {
+        *end = '\0';
+        char * name = rstrip(start);
+        char * value = lskip(end + 1);
+        end = find_char_or_comment(value, '\0');
+        if (*end == ';')
+          *end = '\0';
+        rstrip(value);
+        strncpy0(prev_name, name, sizeof prev_name);
+        map_set(m, section, name, value);
+      }
+    }
+  }
+  fclose(f);
+  return 0;
+}
+
+/* INIReader.cpp:57-66 */
+static long
+get_integer(const cfgmap_t * m, const char * s, const char * n, long dflt)
+{
+  const char * v = map_get(m, s, n);
+  if (!v)
+    v = "";
+  char * end;
+  long   x = strtol(v, &end, 0);
+  return end > v ? x : dflt;
+}
+/* ConfigMap.cpp:32-40 — NB the default is a float argument too */
+static float
+get_float(const cfgmap_t * m, const char * s, const char * n, float dflt)
+{
+  const char * v = map_get(m, s, n);
+  if (!v)
+    v = "";
+  char * end;
+  float  x = strtof(v, &end);
+  return end > v ? x : dflt;
+}
+/* ConfigMap.cpp:58-76 */
+static int
+get_bool(const cfgmap_t * m, const char * s, const char * n, int dflt)
+{
+  const char * v = map_get(m, s, n);
+  if (!v)
+    v = "";
+  int val = dflt;
+  if (!strcmp(v, "1") || !strcmp(v, "yes") || !strcmp(v, "true") || !strcmp(v, "on"))
+    val = 1;
+  if (!strcmp(v, "0") || !strcmp(v, "no") || !strcmp(v, "false") || !strcmp(v, "off"))
+    val = 0;
+  if (!*v)
+    val = dflt;
+  return val;
+}
+static const char *
+get_string(const cfgmap_t * m, const char * s, const char * n, const char * dflt)
+{
+  const char * v = map_get(m, s, n);
+  return v ? v : dflt;
+}
+
+int
+e2do_params_from_ini(const char * path, e2do_params * p)
+{
+  cfgmap_t m = { 0, 0, 0 };
+  int      rc = ini_parse_file(path, &m);
+  memset(p, 0, sizeof *p);
+
+  /* HydroParams ctor defaults that setup() does not overwrite (HydroParams.h:224-232) */
+  p->enableOutput = 1;
+  p->ghostWidth = 2;
+  p->imin = 0;
+  p->jmin = 0;
+
+  /* HydroParams.cpp:47-61 */
+  p->nStepmax = (int)get_integer(&m, "run", "nstepmax", 1000);
+  p->tEnd = get_float(&m, "run", "tend", 0.0);
+  p->nOutput = (int)get_integer(&m, "run", "noutput", 100);
+  if (p->nOutput == -1)
+    p->enableOutput = 0;
+  p->ioHDF5 = get_bool(&m, "run", "use_HDF5", 0);
+  p->ioVTK = get_bool(&m, "run", "use_VTK", 1);
+
+  /* HydroParams.cpp:63-80 */
+  p->nx = (int)get_integer(&m, "mesh", "nx", 2);
+  p->ny = (int)get_integer(&m, "mesh", "ny", 2);
+  p->xmin = get_float(&m, "mesh", "xmin", 0.0);
+  p->ymin = get_float(&m, "mesh", "ymin", 0.0);
+  p->xmax = get_float(&m, "mesh", "xmax", 1.0);
+  p->ymax = get_float(&m, "mesh", "ymax", 1.0);
+  p->boundary_type_xmin = (int)get_integer(&m, "mesh", "boundary_type_xmin", E2DO_BC_DIRICHLET);
+  p->boundary_type_xmax = (int)get_integer(&m, "mesh", "boundary_type_xmax", E2DO_BC_DIRICHLET);
+  p->boundary_type_ymin = (int)get_integer(&m, "mesh", "boundary_type_ymin", E2DO_BC_DIRICHLET);
+  p->boundary_type_ymax = (int)get_integer(&m, "mesh", "boundary_type_ymax", E2DO_BC_DIRICHLET);
+
+  /* HydroParams.cpp:82-105 */
+  p->gamma0 = get_float(&m, "hydro", "gamma0", 1.4);
+  p->cfl = get_float(&m, "hydro", "cfl", 0.5);
+  p->slope_type = get_float(&m, "hydro", "slope_type", 1.0);
+  p->smallc = get_float(&m, "hydro", "smallc", 1e-10);
+  p->smallr = get_float(&m, "hydro", "smallr", 1e-10);
+  p->niter_riemann = (int)get_integer(&m, "hydro", "niter_riemann", 10);
+  const char * rs = get_string(&m, "hydro", "riemann", "approx");
+  if (!strcmp(rs, "approx"))
+    p->riemannSolverType = E2DO_RIEMANN_APPROX;
+  else if (!strcmp(rs, "hll"))
+    p->riemannSolverType = E2DO_RIEMANN_HLL;
+  else if (!strcmp(rs, "hllc"))
+    p->riemannSolverType = E2DO_RIEMANN_HLLC;
+  else
+    p->riemannSolverType = E2DO_RIEMANN_APPROX;
+
+  /* HydroParams.cpp:107-134 */
+  const char * ps = get_string(&m, "hydro", "problem", "unknown");
+  if (!strcmp(ps, "implode"))
+    p->problemType = E2DO_PROBLEM_IMPLODE;
+  else if (!strcmp(ps, "blast"))
+    p->problemType = E2DO_PROBLEM_BLAST;
+  else if (!strcmp(ps, "four_quadrant"))
+    p->problemType = E2DO_PROBLEM_FOUR_QUADRANT;
+  else if (!strcmp(ps, "discontinuity"))
+    p->problemType = E2DO_PROBLEM_DISCONTINUITY;
+  else if (!strcmp(ps, "shocked_bubble"))
+  {
+    p->problemType = E2DO_PROBLEM_SHOCKED_BUBBLE;
+    /* HydroParams.cpp:19-38 */
+    p->bubble_radius = get_float(&m, "shocked_bubble", "bubble_radius", 0.025);
+    p->bubble_center_x = get_float(&m, "shocked_bubble", "bubble_center_x", 0.225);
+    p->bubble_center_y = get_float(&m, "shocked_bubble", "bubble_center_y", 0.0445);
+    p->bubble_density = get_float(&m, "shocked_bubble", "bubble_density", 3.863);
+    p->bubble_pressure = get_float(&m, "shocked_bubble", "bubble_pressure", 1.0132e5);
+    p->preshock_density = get_float(&m, "shocked_bubble", "preshock_density", 1.225);
+    p->preshock_pressure = get_float(&m, "shocked_bubble", "preshock_pressure", 1.0132e5);
+    p->postshock_density = get_float(&m, "shocked_bubble", "postshock_density", 1.686);
+    p->postshock_pressure = get_float(&m, "shocked_bubble", "postshock_pressure", 1.59e5);
+    p->postshock_velocity = get_float(&m, "shocked_bubble", "postshock_velocity", 113.5);
+    p->shock_loc = get_float(&m, "shocked_bubble", "shock_loc", 0.170);
+  }
+  else
+    p->problemType = E2DO_PROBLEM_IMPLODE;
+
+  /* HydroParams.cpp:136-144 — defaults are computed in double, then narrowed to float */
+  p->blast_radius = get_float(&m, "blast", "radius", (float)((p->xmin + p->xmax) / 2.0 / 10));
+  p->blast_center_x = get_float(&m, "blast", "center_x", (float)((p->xmin + p->xmax) / 2));
+  p->blast_center_y = get_float(&m, "blast", "center_y", (float)((p->ymin + p->ymax) / 2));
+  p->blast_density_in = get_float(&m, "blast", "density_in", 1.0);
+  p->blast_density_out = get_float(&m, "blast", "density_out", 1.2);
+  p->blast_pressure_in = get_float(&m, "blast", "pressure_in", 10.0);
+  p->blast_pressure_out = get_float(&m, "blast", "pressure_out", 0.1);
+  p->blast_total_energy_inside = get_float(&m, "blast", "total_energy_inside", 0.0);
+  p->blast_nbins = (int)get_integer(&m, "blast", "nbins", 100);
+
+  /* HydroParams.cpp:146-152 (float -> int) */
+  p->implementationVersion = (int)get_float(&m, "OTHER", "implementationVersion", 0);
+  if (p->implementationVersion != 0 && p->implementationVersion != 1 && p->implementationVersion != 2)
+    p->implementationVersion = 0;
+
+  /* HydroParams::init, HydroParams.cpp:161-174 */
+  p->imax = p->nx - 1 + 2 * p->ghostWidth;
+  p->jmax = p->ny - 1 + 2 * p->ghostWidth;
+  p->isize = p->imax - p->imin + 1;
+  p->jsize = p->jmax - p->jmin + 1;
+  p->dx = (p->xmax - p->xmin) / p->nx;
+  p->dy = (p->ymax - p->ymin) / p->ny;
+  p->smallp = p->smallc * p->smallc / p->gamma0;
+  p->smallpp = p->smallr * p->smallp;
+  p->gamma6 = (p->gamma0 + 1.0) / (2.0 * p->gamma0);
+
+  map_free(&m);
+  return rc;
+}
+
+/* ===================================================================================== */
+/* per-cell math, src/HydroBaseFunctor.h                                                  */
+/* ===================================================================================== */
+
+/* HydroBaseFunctor.h:76-102 */
+void
+e2do_compute_primitives(const e2do_params * p, const double u[4], double * c, double q[4])
+{
+  const double gamma0 = p->gamma0, smallr = p->smallr, smallp = p->smallp;
+  double       d = fmax(u[ID], smallr);
+  double       ux = u[IU] / d;
+  double       uy = u[IV] / d;
+  double       eken = 0.5 * (ux * ux + uy * uy);
+  double       e = u[IP] / d - eken;
+  double       pr = fmax((gamma0 - 1.0) * d * e, d * smallp);
+  *c = sqrt(gamma0 * pr / d);
+  q[ID] = d;
+  q[IP] = pr;
+  q[IU] = ux;
+  q[IV] = uy;
+}
+
+/* HydroBaseFunctor.h:419-455 (one variable, one direction) */
+static inline double
+slope_scalar(double slope_type, double q, double qp, double qm)
+{
+  double dlft = slope_type * (q - qm);
+  double drgt = slope_type * (qp - q);
+  double dcen = 0.5 * (qp - qm);
+  double dsgn = (dcen >= 0.0) ? 1.0 : -1.0;
+  double slop = fmin(fabs(dlft), fabs(drgt));
+  double dlim = slop;
+  if ((dlft * drgt) <= 0.0)
+    dlim = 0.0;
+  return dsgn * fmin(dlim, fabs(dcen));
+}
+
+/* HydroBaseFunctor.h:473-516.  slope_type outside {0,1,2} leaves dq untouched in the reference
+ * (uninitialised there); here the outputs are left as passed in. */
+void
+e2do_slope_unsplit_hydro_2d(const e2do_params * p, const double q[4], const double qPlusX[4],
+                            const double qMinusX[4], const double qPlusY[4], const double qMinusY[4],
+                            double dqX[4], double dqY[4])
+{
+  const double st = p->slope_type;
+  if (st == 0)
+  {
+    for (int v = 0; v < 4; ++v)
+      dqX[v] = dqY[v] = 0.0;
+    return;
+  }
+  if (st == 1 || st == 2)
+    for (int v = 0; v < 4; ++v)
+    {
+      dqX[v] = slope_scalar(st, q[v], qPlusX[v], qMinusX[v]);
+      dqY[v] = slope_scalar(st, q[v], qPlusY[v], qMinusY[v]);
+    }
+}
+
+/* HydroBaseFunctor.h:214-291 */
+void
+e2do_trace_unsplit_2d_along_dir(const e2do_params * p, const double q[4], const double dqX[4],
+                                const double dqY[4], double dtdx, double dtdy, int faceId, double qface[4])
+{
+  const double gamma0 = p->gamma0, smallr = p->smallr;
+  double       r = q[ID], pp = q[IP], u = q[IU], v = q[IV];
+  double       drx = dqX[ID], dpx = dqX[IP], dux = dqX[IU], dvx = dqX[IV];
+  double       dry = dqY[ID], dpy = dqY[IP], duy = dqY[IU], dvy = dqY[IV];
+
+  double sr0 = -u * drx - v * dry - (dux + dvy) * r;
+  double sp0 = -u * dpx - v * dpy - (dux + dvy) * gamma0 * pp;
+  double su0 = -u * dux - v * duy - (dpx) / r;
+  double sv0 = -u * dvx - v * dvy - (dpy) / r;
+
+  if (faceId == E2DO_FACE_XMIN)
+  {
+    qface[ID] = r - 0.5 * drx + sr0 * dtdx * 0.5;
+    qface[IP] = pp - 0.5 * dpx + sp0 * dtdx * 0.5;
+    qface[IU] = u - 0.5 * dux + su0 * dtdx * 0.5;
+    qface[IV] = v - 0.5 * dvx + sv0 * dtdx * 0.5;
+    qface[ID] = fmax(smallr, qface[ID]);
+  }
+  if (faceId == E2DO_FACE_XMAX)
+  {
+    qface[ID] = r + 0.5 * drx + sr0 * dtdx * 0.5;
+    qface[IP] = pp + 0.5 * dpx + sp0 * dtdx * 0.5;
+    qface[IU] = u + 0.5 * dux + su0 * dtdx * 0.5;
+    qface[IV] = v + 0.5 * dvx + sv0 * dtdx * 0.5;
+    qface[ID] = fmax(smallr, qface[ID]);
+  }
+  if (faceId == E2DO_FACE_YMIN)
+  {
+    qface[ID] = r - 0.5 * dry + sr0 * dtdy * 0.5;
+    qface[IP] = pp - 0.5 * dpy + sp0 * dtdy * 0.5;
+    qface[IU] = u - 0.5 * duy + su0 * dtdy * 0.5;
+    qface[IV] = v - 0.5 * dvy + sv0 * dtdy * 0.5;
+    qface[ID] = fmax(smallr, qface[ID]);
+  }
+  if (faceId == E2DO_FACE_YMAX)
+  {
+    qface[ID] = r + 0.5 * dry + sr0 * dtdy * 0.5;
+    qface[IP] = pp + 0.5 * dpy + sp0 * dtdy * 0.5;
+    qface[IU] = u + 0.5 * duy + su0 * dtdy * 0.5;
+    qface[IV] = v + 0.5 * dvy + sv0 * dtdy * 0.5;
+    qface[ID] = fmax(smallr, qface[ID]);
+  }
+}
+
+/* HydroBaseFunctor.h:523-547 */
+void
+e2do_cmpflx(const e2do_params * p, const double qgdnv[4], double flux[4])
+{
+  const double gamma0 = p->gamma0;
+  flux[ID] = qgdnv[ID] * qgdnv[IU];
+  flux[IU] = flux[ID] * qgdnv[IU] + qgdnv[IP];
+  flux[IV] = flux[ID] * qgdnv[IV];
+  double entho = 1.0 / (gamma0 - 1.0);
+  double ekin = 0.5 * qgdnv[ID] * (qgdnv[IU] * qgdnv[IU] + qgdnv[IV] * qgdnv[IV]);
+  double etot = qgdnv[IP] * entho + ekin;
+  flux[IP] = qgdnv[IU] * (etot + qgdnv[IP]);
+}
+
+/* HydroBaseFunctor.h:558-693 — dead code in the reference (never called by a kernel), restated
+ * because the north star names it.  NB: the iteration cap is the literal 10 and the tolerance the
+ * literal 1e-6 (HydroBaseFunctor.h:592), not niter_riemann. */
+void
+e2do_riemann_approx(const e2do_params * p, const double qleft[4], const double qright[4], double qgdnv[4],
+                    double flux[4])
+{
+  const double gamma0 = p->gamma0, gamma6 = p->gamma6, smallr = p->smallr, smallc = p->smallc;
+  const double smallp = p->smallp, smallpp = p->smallpp;
+
+  double rl = fmax(qleft[ID], smallr);
+  double ul = qleft[IU];
+  double pl = fmax(qleft[IP], rl * smallp);
+  double rr = fmax(qright[ID], smallr);
+  double ur = qright[IU];
+  double pr = fmax(qright[IP], rr * smallp);
+
+  double cl = gamma0 * pl * rl;
+  double cr = gamma0 * pr * rr;
+
+  double wl = sqrt(cl);
+  double wr = sqrt(cr);
+  double pstar = fmax(((wr * pl + wl * pr) + wl * wr * (ul - ur)) / (wl + wr), 0.0);
+  double pold = pstar;
+  double conv = 1.0;
+
+  for (int iter = 0; (iter < 10) && (conv > 1e-6); ++iter)
+  {
+    double wwl = sqrt(cl * (1.0 + gamma6 * (pold - pl) / pl));
+    double wwr = sqrt(cr * (1.0 + gamma6 * (pold - pr) / pr));
+    double ql = 2.0f * wwl * wwl * wwl / (wwl * wwl + cl);
+    double qr = 2.0f * wwr * wwr * wwr / (wwr * wwr + cr);
+    double usl = ul - (pold - pl) / wwl;
+    double usr = ur + (pold - pr) / wwr;
+    double delp = fmax(qr * ql / (qr + ql) * (usl - usr), -pold);
+    pold = pold + delp;
+    conv = fabs(delp / (pold + smallpp));
+  }
+
+  pstar = pold;
+  wl = sqrt(cl * (1.0 + gamma6 * (pstar - pl) / pl));
+  wr = sqrt(cr * (1.0 + gamma6 * (pstar - pr) / pr));
+
+  double ustar = 0.5 * (ul + (pl - pstar) / wl + ur - (pr - pstar) / wr);
+  double sgnm = copysign(1.0, ustar);
+
+  double ro, uo, po, wo;
+  if (sgnm > 0.0)
+  {
+    ro = rl;
+    uo = ul;
+    po = pl;
+    wo = wl;
+  }
+  else
+  {
+    ro = rr;
+    uo = ur;
+    po = pr;
+    wo = wr;
+  }
+  double co = fmax(smallc, sqrt(fabs(gamma0 * po / ro)));
+  double rstar = fmax((double)(ro / (1.0 + ro * (po - pstar) / (wo * wo))), (double)(smallr));
+  double cstar = fmax(smallc, sqrt(fabs(gamma0 * pstar / rstar)));
+
+  double spout = co - sgnm * uo;
+  double spin = cstar - sgnm * ustar;
+  double ushock = wo / ro - sgnm * uo;
+  if (pstar >= po)
+  {
+    spin = ushock;
+    spout = ushock;
+  }
+
+  double scr = fmax(spout - spin, smallc + fabs(spout + spin));
+  double frac = 0.5 * (1.0 + (spout + spin) / scr);
+  if (frac != frac)
+    frac = 0.0;
+  else
+    frac = frac >= 1.0 ? 1.0 : frac <= 0.0 ? 0.0 : frac;
+
+  qgdnv[ID] = frac * rstar + (1.0 - frac) * ro;
+  qgdnv[IU] = frac * ustar + (1.0 - frac) * uo;
+  qgdnv[IP] = frac * pstar + (1.0 - frac) * po;
+  if (spout < 0.0)
+  {
+    qgdnv[ID] = ro;
+    qgdnv[IU] = uo;
+    qgdnv[IP] = po;
+  }
+  if (spin > 0.0)
+  {
+    qgdnv[ID] = rstar;
+    qgdnv[IU] = ustar;
+    qgdnv[IP] = pstar;
+  }
+  if (sgnm > 0.0)
+    qgdnv[IV] = qleft[IV];
+  else
+    qgdnv[IV] = qright[IV];
+
+  e2do_cmpflx(p, qgdnv, flux);
+}
+
+/* HydroBaseFunctor.h:704-809 (qgdnv is never written by the reference) */
+void
+e2do_riemann_hllc(const e2do_params * p, const double qleft[4], const double qright[4], double flux[4])
+{
+  const double gamma0 = p->gamma0, smallr = p->smallr, smallp = p->smallp, smallc = p->smallc;
+  const double entho = 1.0 / (gamma0 - 1.0);
+
+  double rl = fmax(qleft[ID], smallr);
+  double pl = fmax(qleft[IP], rl * smallp);
+  double ul = qleft[IU];
+  double ecinl = 0.5 * rl * ul * ul;
+  ecinl += 0.5 * rl * qleft[IV] * qleft[IV];
+  double etotl = pl * entho + ecinl;
+  double ptotl = pl;
+
+  double rr = fmax(qright[ID], smallr);
+  double pr = fmax(qright[IP], rr * smallp);
+  double ur = qright[IU];
+  double ecinr = 0.5 * rr * ur * ur;
+  ecinr += 0.5 * rr * qright[IV] * qright[IV];
+  double etotr = pr * entho + ecinr;
+  double ptotr = pr;
+
+  double cfastl = sqrt(fmax(gamma0 * pl / rl, smallc * smallc));
+  double cfastr = sqrt(fmax(gamma0 * pr / rr, smallc * smallc));
+
+  double SL = fmin(ul, ur) - fmax(cfastl, cfastr);
+  double SR = fmax(ul, ur) + fmax(cfastl, cfastr);
+
+  double rcl = rl * (ul - SL);
+  double rcr = rr * (SR - ur);
+
+  double ustar = (rcr * ur + rcl * ul + (ptotl - ptotr)) / (rcr + rcl);
+  double ptotstar = (rcr * ptotl + rcl * ptotr + rcl * rcr * (ul - ur)) / (rcr + rcl);
+
+  double rstarl = rl * (SL - ul) / (SL - ustar);
+  double etotstarl = ((SL - ul) * etotl - ptotl * ul + ptotstar * ustar) / (SL - ustar);
+  double rstarr = rr * (SR - ur) / (SR - ustar);
+  double etotstarr = ((SR - ur) * etotr - ptotr * ur + ptotstar * ustar) / (SR - ustar);
+
+  double ro, uo, ptoto, etoto;
+  if (SL > 0.0)
+  {
+    ro = rl;
+    uo = ul;
+    ptoto = ptotl;
+    etoto = etotl;
+  }
+  else if (ustar > 0.0)
+  {
+    ro = rstarl;
+    uo = ustar;
+    ptoto = ptotstar;
+    etoto = etotstarl;
+  }
+  else if (SR > 0.0)
+  {
+    ro = rstarr;
+    uo = ustar;
+    ptoto = ptotstar;
+    etoto = etotstarr;
+  }
+  else
+  {
+    ro = rr;
+    uo = ur;
+    ptoto = ptotr;
+    etoto = etotr;
+  }
+
+  flux[ID] = ro * uo;
+  flux[IU] = ro * uo * uo + ptoto;
+  flux[IP] = (etoto + ptoto) * uo;
+  if (flux[ID] > 0.0)
+    flux[IV] = flux[ID] * qleft[IV];
+  else
+    flux[IV] = flux[ID] * qright[IV];
+}
+
+/* ===================================================================================== */
+/* array-level operators, src/HydroRunFunctors.h                                          */
+/* ===================================================================================== */
+#define AT(A, i, j, v) (A)[(size_t)(i) + (size_t)isize * ((size_t)(j) + (size_t)jsize * (size_t)(v))]
+
+static void
+load4(const double * A, int isize, int jsize, int i, int j, double s[4])
+{
+  for (int v = 0; v < 4; ++v)
+    s[v] = AT(A, i, j, v);
+}
+
+/* Init*Functor, HydroRunFunctors.h:1347-1827; cell centre as :1384-1385 with the GLOBAL row index */
+void
+e2do_init_slab(const e2do_params * p, double * U, int jsize, int j_off)
+{
+  const int    isize = p->isize, gw = p->ghostWidth;
+  const double xmin = p->xmin, ymin = p->ymin, dx = p->dx, dy = p->dy, gamma0 = p->gamma0;
+
+  if (p->problemType == E2DO_PROBLEM_BLAST)
+  { /* :1466-1545 */
+    const double radius2 = p->blast_radius * p->blast_radius;
+    double       volume = 0.0; /* reduction order is unspecified in the reference; serial here */
+    for (int j = 0; j < jsize; ++j)
+      for (int i = 0; i < isize; ++i)
+      {
+        double x = xmin + dx / 2 + (i - gw) * dx;
+        double y = ymin + dy / 2 + (j + j_off - gw) * dy;
+        double d2 = (x - p->blast_center_x) * (x - p->blast_center_x) +
+                    (y - p->blast_center_y) * (y - p->blast_center_y);
+        if (d2 < radius2)
+        {
+          AT(U, i, j, ID) = p->blast_density_in;
+          AT(U, i, j, IP) = p->blast_pressure_in / (gamma0 - 1.0);
+          volume += dx * dy;
+        }
+        else
+        {
+          AT(U, i, j, ID) = p->blast_density_out;
+          AT(U, i, j, IP) = p->blast_pressure_out / (gamma0 - 1.0);
+        }
+        AT(U, i, j, IU) = 0.0;
+        AT(U, i, j, IV) = 0.0;
+      }
+    if (p->blast_total_energy_inside > 0)
+      for (int j = 0; j < jsize; ++j)
+        for (int i = 0; i < isize; ++i)
+        {
+          double x = xmin + dx / 2 + (i - gw) * dx;
+          double y = ymin + dy / 2 + (j + j_off - gw) * dy;
+          double d2 = (x - p->blast_center_x) * (x - p->blast_center_x) +
+                      (y - p->blast_center_y) * (y - p->blast_center_y);
+          if (d2 < radius2)
+            AT(U, i, j, IP) = p->blast_total_energy_inside / volume;
+        }
+    return;
+  }
+
+  /* four-quadrant states, :1578-1623 */
+  double Q4[4][4] = { { 1.5, 1.5, 0.0, 0.0 },
+                      { 0.5323, 0.3, 1.206, 0.0 },
+                      { 0.138, 0.029, 1.206, 1.206 },
+                      { 0.5323, 0.3, 0.0, 1.206 } };
+  for (int k = 0; k < 4; ++k)
+  {
+    double rho = Q4[k][ID], pr = Q4[k][IP], u = Q4[k][IU], v = Q4[k][IV];
+    Q4[k][IU] *= rho;
+    Q4[k][IV] *= rho;
+    Q4[k][IP] = pr / (gamma0 - 1.0) + rho * (u * u + v * v) * 0.5;
+  }
+
+  for (int j = 0; j < jsize; ++j)
+    for (int i = 0; i < isize; ++i)
+    {
+      double x = xmin + dx / 2 + (i - gw) * dx;
+      double y = ymin + dy / 2 + (j + j_off - gw) * dy;
+      double u[4] = { 0, 0, 0, 0 };
+      switch (p->problemType)
+      {
+        case E2DO_PROBLEM_FOUR_QUADRANT:
+        { /* :1625-1665 */
+          const double xt = 0.8, yt = 0.8;
+          int          k = (x < xt) ? ((y < yt) ? 2 : 1) : ((y < yt) ? 3 : 0);
+          for (int v = 0; v < 4; ++v)
+            u[v] = Q4[k][v];
+          break;
+        }
+        case E2DO_PROBLEM_DISCONTINUITY:
+        { /* :1713-1729 */
+          if (x + y < 1)
+            u[ID] = 1.0 + x * x;
+          else
+            u[ID] = 0.25;
+          u[IP] = 1.0 / (gamma0 - 1.0);
+          break;
+        }
+        case E2DO_PROBLEM_SHOCKED_BUBBLE:
+        { /* :1776-1820 */
+          double pres;
+          if (x < p->shock_loc)
+          {
+            u[ID] = p->postshock_density;
+            u[IU] = p->postshock_density * p->postshock_velocity;
+            pres = p->postshock_pressure;
+          }
+          else
+          {
+            double radius = sqrt((x - p->bubble_center_x) * (x - p->bubble_center_x) +
+                                 (y - p->bubble_center_y) * (y - p->bubble_center_y));
+            if (radius < p->bubble_radius)
+            {
+              u[ID] = p->bubble_density;
+              pres = p->bubble_pressure;
+            }
+            else
+            {
+              u[ID] = p->preshock_density;
+              pres = p->preshock_pressure;
+            }
+          }
+          u[IV] = 0.0;
+          double rho_eint = pres / (gamma0 - 1);
+          u[IE] = rho_eint + 0.5 * (u[IU] * u[IU] + u[IV] * u[IV]) / u[ID];
+          break;
+        }
+        case E2DO_PROBLEM_IMPLODE:
+        default:
+        { /* :1384-1401 */
+          double tmp = x + y * y;
+          if (tmp > 0.5 && tmp < 1.5)
+          {
+            u[ID] = 1.0;
+            u[IP] = 1.0 / (gamma0 - 1.0);
+          }
+          else
+          {
+            u[ID] = 0.125;
+            u[IP] = 0.14 / (gamma0 - 1.0);
+          }
+          break;
+        }
+      }
+      for (int v = 0; v < 4; ++v)
+        AT(U, i, j, v) = u[v];
+    }
+}
+
+/* MakeBoundariesFunctor<face>, HydroRunFunctors.h:1832-2030, in the order of HydroRun.h:394-397.
+ * `ny` in the reference's index formulas is the slab's own interior row count here. */
+void
+e2do_make_boundaries_slab(const e2do_params * p, double * U, int jsize, int do_ymin, int do_ymax)
+{
+  const int isize = p->isize, gw = p->ghostWidth, nx = p->nx, ny = jsize - 2 * gw;
+
+  /* XMIN :1876-1911 */
+  for (int j = 0; j < jsize; ++j)
+    for (int i = 0; i < gw; ++i)
+      for (int v = 0; v < 4; ++v)
+      {
+        double sign = 1.0;
+        int    i0;
+        if (p->boundary_type_xmin == E2DO_BC_DIRICHLET)
+        {
+          i0 = 2 * gw - 1 - i;
+          if (v == IU)
+            sign = -1.0;
+        }
+        else if (p->boundary_type_xmin == E2DO_BC_NEUMANN)
+          i0 = gw;
+        else
+          i0 = nx + i;
+        AT(U, i, j, v) = AT(U, i0, j, v) * sign;
+      }
+  /* XMAX :1913-1949 */
+  for (int j = 0; j < jsize; ++j)
+    for (int i = nx + gw; i <= nx + 2 * gw - 1; ++i)
+      for (int v = 0; v < 4; ++v)
+      {
+        double sign = 1.0;
+        int    i0;
+        if (p->boundary_type_xmax == E2DO_BC_DIRICHLET)
+        {
+          i0 = 2 * nx + 2 * gw - 1 - i;
+          if (v == IU)
+            sign = -1.0;
+        }
+        else if (p->boundary_type_xmax == E2DO_BC_NEUMANN)
+          i0 = nx + gw - 1;
+        else
+          i0 = i - nx;
+        AT(U, i, j, v) = AT(U, i0, j, v) * sign;
+      }
+  /* YMIN :1951-1986 (all i, so corners take the x-filled values) */
+  if (do_ymin)
+    for (int i = 0; i < isize; ++i)
+      for (int j = 0; j < gw; ++j)
+        for (int v = 0; v < 4; ++v)
+        {
+          double sign = 1.0;
+          int    j0;
+          if (p->boundary_type_ymin == E2DO_BC_DIRICHLET)
+          {
+            j0 = 2 * gw - 1 - j;
+            if (v == IV)
+              sign = -1.0;
+          }
+          else if (p->boundary_type_ymin == E2DO_BC_NEUMANN)
+            j0 = gw;
+          else
+            j0 = ny + j;
+          AT(U, i, j, v) = AT(U, i, j0, v) * sign;
+        }
+  /* YMAX :1988-2024 */
+  if (do_ymax)
+    for (int i = 0; i < isize; ++i)
+      for (int j = ny + gw; j <= ny + 2 * gw - 1; ++j)
+        for (int v = 0; v < 4; ++v)
+        {
+          double sign = 1.0;
+          int    j0;
+          if (p->boundary_type_ymax == E2DO_BC_DIRICHLET)
+          {
+            j0 = 2 * ny + 2 * gw - 1 - j;
+            if (v == IV)
+              sign = -1.0;
+          }
+          else if (p->boundary_type_ymax == E2DO_BC_NEUMANN)
+            j0 = ny + gw - 1;
+          else
+            j0 = j - ny;
+          AT(U, i, j, v) = AT(U, i, j0, v) * sign;
+        }
+}
+
+/* ComputeDtFunctor, HydroRunFunctors.h:17-79: max over interior cells; Kokkos::Max starts at -inf */
+double
+e2do_compute_invdt_slab(const e2do_params * p, const double * U, int jsize)
+{
+  const int isize = p->isize, gw = p->ghostWidth;
+  double    invDt = -INFINITY;
+#pragma omp parallel for schedule(static) reduction(max : invDt)
+  for (int j = gw; j < jsize - gw; ++j)
+    for (int i = gw; i < isize - gw; ++i)
+    {
+      double u[4], q[4], c;
+      load4(U, isize, jsize, i, j, u);
+      e2do_compute_primitives(p, u, &c, q);
+      double vx = c + fabs(q[IU]);
+      double vy = c + fabs(q[IV]);
+      invDt = fmax(invDt, vx / p->dx + vy / p->dy);
+    }
+  return invDt;
+}
+
+/* ConvertToPrimitivesFunctor, HydroRunFunctors.h:84-143: whole array incl. ghosts */
+void
+e2do_convert_to_primitives_slab(const e2do_params * p, const double * U, double * Q, int jsize)
+{
+  const int isize = p->isize;
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < jsize; ++j)
+    for (int i = 0; i < isize; ++i)
+    {
+      double u[4], q[4], c;
+      load4(U, isize, jsize, i, j, u);
+      e2do_compute_primitives(p, u, &c, q);
+      for (int v = 0; v < 4; ++v)
+        AT(Q, i, j, v) = q[v];
+    }
+}
+
+static void
+slopes_at(const e2do_params * p, const double * Q, int isize, int jsize, int i, int j, double q[4],
+          double dqX[4], double dqY[4])
+{
+  double qpx[4], qmx[4], qpy[4], qmy[4];
+  load4(Q, isize, jsize, i, j, q);
+  load4(Q, isize, jsize, i + 1, j, qpx);
+  load4(Q, isize, jsize, i - 1, j, qmx);
+  load4(Q, isize, jsize, i, j + 1, qpy);
+  load4(Q, isize, jsize, i, j - 1, qmy);
+  e2do_slope_unsplit_hydro_2d(p, q, qpx, qmx, qpy, qmy, dqX, dqY);
+}
+
+static void
+swap2(double * a, double * b)
+{
+  double t = *a;
+  *a = *b;
+  *b = t;
+}
+
+/* ComputeAndStoreFluxesFunctor, HydroRunFunctors.h:412-651 */
+void
+e2do_compute_and_store_fluxes_slab(const e2do_params * p, const double * Q, double * Fx, double * Fy,
+                                   double dtdx, double dtdy, int jsize)
+{
+  const int isize = p->isize, gw = p->ghostWidth;
+#pragma omp parallel for schedule(static)
+  for (int j = gw; j <= jsize - gw; ++j)
+    for (int i = gw; i <= isize - gw; ++i)
+    {
+      double q[4], dqX[4], dqY[4], qn[4], dqXn[4], dqYn[4], qleft[4], qright[4], flux[4];
+      for (int v = 0; v < 4; ++v) /* slope_type outside {0,1,2}: undefined in the reference; zero here */
+        dqX[v] = dqY[v] = dqXn[v] = dqYn[v] = 0.0;
+
+      slopes_at(p, Q, isize, jsize, i, j, q, dqX, dqY);         /* :491-517 */
+      slopes_at(p, Q, isize, jsize, i - 1, j, qn, dqXn, dqYn);  /* :521-552 */
+      e2do_trace_unsplit_2d_along_dir(p, q, dqX, dqY, dtdx, dtdy, E2DO_FACE_XMIN, qright);   /* :559 */
+      e2do_trace_unsplit_2d_along_dir(p, qn, dqXn, dqYn, dtdx, dtdy, E2DO_FACE_XMAX, qleft); /* :562 */
+      e2do_riemann_hllc(p, qleft, qright, flux);                                             /* :567 */
+      for (int v = 0; v < 4; ++v)
+        AT(Fx, i, j, v) = flux[v] * dtdx; /* :572-575 */
+
+      slopes_at(p, Q, isize, jsize, i, j - 1, qn, dqXn, dqYn);  /* :583-614 */
+      e2do_trace_unsplit_2d_along_dir(p, q, dqX, dqY, dtdx, dtdy, E2DO_FACE_YMIN, qright);   /* :621 */
+      e2do_trace_unsplit_2d_along_dir(p, qn, dqXn, dqYn, dtdx, dtdy, E2DO_FACE_YMAX, qleft); /* :624 */
+      swap2(&qleft[IU], &qleft[IV]);   /* :628-632 */
+      swap2(&qright[IU], &qright[IV]);
+      e2do_riemann_hllc(p, qleft, qright, flux);
+      swap2(&flux[IU], &flux[IV]);
+      for (int v = 0; v < 4; ++v)
+        AT(Fy, i, j, v) = flux[v] * dtdy; /* :637-640 */
+    }
+}
+
+/* UpdateFunctor, HydroRunFunctors.h:656-723 — the order of the four += / -= is part of the contract */
+void
+e2do_update_slab(const e2do_params * p, double * U, const double * Fx, const double * Fy, int jsize)
+{
+  const int isize = p->isize, gw = p->ghostWidth;
+#pragma omp parallel for schedule(static)
+  for (int j = gw; j < jsize - gw; ++j)
+    for (int i = gw; i < isize - gw; ++i)
+      for (int v = 0; v < 4; ++v)
+      {
+        double x = AT(U, i, j, v);
+        x += AT(Fx, i, j, v);
+        x -= AT(Fx, i + 1, j, v);
+        x += AT(Fy, i, j, v);
+        x -= AT(Fy, i, j + 1, v);
+        AT(U, i, j, v) = x;
+      }
+}
+
+/* HydroRun::godunov_unsplit_impl for implementationVersion 0, HydroRun.h:281-331, without :296 */
+void
+e2do_godunov_slab(const e2do_params * p, const double * Uin, double * Uout, double * work, double dt, int jsize)
+{
+  const size_t n = (size_t)p->isize * (size_t)jsize * 4;
+  double *     Q = work;
+  double *     Fx = work + n;
+  double *     Fy = work + 2 * n;
+  double       dtdx = dt / p->dx; /* :290-291 */
+  double       dtdy = dt / p->dy;
+  memcpy(Uout, Uin, n * sizeof(double)); /* :302 */
+  e2do_convert_to_primitives_slab(p, Uin, Q, jsize); /* :309 */
+  e2do_compute_and_store_fluxes_slab(p, Q, Fx, Fy, dtdx, dtdy, jsize); /* :319 */
+  e2do_update_slab(p, Uout, Fx, Fy, jsize); /* :326 */
+}
+
+/* main.cpp:86-143 */
+int
+e2do_run(const e2do_params * p, double * U, double * U2, long max_steps, double * dt_seq, long dt_cap,
+         double * t_out)
+{
+  const size_t n = (size_t)p->isize * (size_t)p->jsize * 4;
+  const int    jsize = p->jsize;
+  double *     work = (double *)malloc(3 * n * sizeof(double));
+  memset(work, 0, 3 * n * sizeof(double));
+  if (max_steps < 0)
+    max_steps = p->nStepmax;
+
+  e2do_init_slab(p, U, jsize, 0);        /* HydroRun.h:185-211 */
+  memcpy(U2, U, n * sizeof(double));     /* HydroRun.h:214 */
+
+  double t = 0, dt = 0;
+  int    nStep = 0;
+  long   ndt = 0;
+  dt = p->cfl / e2do_compute_invdt_slab(p, U, jsize); /* main.cpp:87 */
+  if (dt_seq && ndt < dt_cap)
+    dt_seq[ndt++] = dt;
+  e2do_make_boundaries_slab(p, U, jsize, 1, 1);  /* main.cpp:90-91 */
+  e2do_make_boundaries_slab(p, U2, jsize, 1, 1);
+
+  while (t < p->tEnd && nStep < max_steps)
+  {
+    double * in = (nStep % 2 == 0) ? U : U2;
+    double * out = (nStep % 2 == 0) ? U2 : U;
+    dt = p->cfl / e2do_compute_invdt_slab(p, in, jsize); /* main.cpp:128, HydroRun.h:246 */
+    if (t + dt > p->tEnd)                                /* main.cpp:131-134 */
+      dt = p->tEnd - t;
+    e2do_make_boundaries_slab(p, in, jsize, 1, 1);       /* HydroRun.h:296 */
+    e2do_godunov_slab(p, in, out, work, dt, jsize);
+    nStep++;
+    t += dt;
+    if (dt_seq && ndt < dt_cap)
+      dt_seq[ndt++] = dt;
+  }
+  free(work);
+  if (t_out)
+    *t_out = t;
+  return nStep;
+}
