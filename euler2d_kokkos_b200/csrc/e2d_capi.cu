@@ -1,0 +1,933 @@
+// C ABI of euler2d_b200 (include/euler2d_b200.h): the HydroRun handle, the device-resident time
+// loop and thin wrappers over the kernel launchers.  No torch types, no exceptions across the ABI.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "e2d_internal.h"
+
+namespace
+{
+
+thread_local std::string               g_last_error;
+std::atomic<unsigned long long>        g_launches{ 0 };
+
+int
+fail_cuda(cudaError_t e, const char * what)
+{
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return E2D_ERR_CUDA;
+}
+
+#define E2D_CUDA(call)                      \
+  do                                        \
+  {                                         \
+    cudaError_t e2d_err_ = (call);          \
+    if (e2d_err_ != cudaSuccess)            \
+      return fail_cuda(e2d_err_, #call);    \
+  } while (0)
+
+int
+fail(int status, const std::string & msg)
+{
+  g_last_error = msg;
+  return status;
+}
+
+} // namespace
+
+namespace e2d
+{
+void
+count_launch(int n)
+{
+  g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed);
+}
+} // namespace e2d
+
+using namespace e2d;
+
+struct e2d_handle
+{
+  e2d_params   p;
+  e2d_slab     slab;
+  bool         whole;
+  Geom         g;
+  size_t       n; // doubles per array
+  cudaStream_t stream = nullptr;
+  bool         own_stream = false;
+  double *     U = nullptr;
+  double *     U2 = nullptr;
+  bool         own_U = false, own_U2 = false;
+  double *     Q = nullptr;  // impl 0/1
+  double *     Fx = nullptr; // impl 0/1
+  double *     Fy = nullptr; // impl 0
+  double *     Sx = nullptr; // impl 1
+  double *     Sy = nullptr; // impl 1
+  // scalars
+  unsigned long long * d_bits = nullptr; // scratch for compute_dt
+  LoopState *          d_loop = nullptr;
+  LoopState *          h_loop = nullptr; // pinned mirror
+  double *             d_hist = nullptr;
+  long                 hist_cap = 0;
+  bool                 loop_primed = false; // d_loop->invdt_cur valid for the current state
+  double               t = 0.0;
+  int                  nStep = 0;
+  double               dt_last = 0.0;
+  // timers: boundaries, godunov, primitive, fluxes, update
+  bool        timing = false;
+  double      timers[5] = { 0, 0, 0, 0, 0 };
+  cudaEvent_t ev[2] = { nullptr, nullptr };
+  cudaEvent_t ev_t[5][2] = {}; // one event pair per timer: the godunov timer nests the others
+};
+
+namespace
+{
+
+int
+faces_for(const e2d_handle * h)
+{
+  if (h->whole)
+    return E2D_FACES_ALL;
+  int f = E2D_FACES_X;
+  // a periodic y direction split over several ranks is closed by the halo exchange, not by a fill
+  if (h->slab.rank == 0 && h->p.boundary_type_ymin != E2D_BC_PERIODIC)
+    f |= E2D_FACES_YMIN;
+  if (h->slab.rank == h->slab.nranks - 1 && h->p.boundary_type_ymax != E2D_BC_PERIODIC)
+    f |= E2D_FACES_YMAX;
+  if (h->slab.nranks == 1)
+    f = E2D_FACES_ALL;
+  return f;
+}
+
+double *
+array_of(e2d_handle * h, int which)
+{
+  switch (which)
+  {
+    case E2D_U:
+      return h->U;
+    case E2D_U2:
+      return h->U2;
+    case E2D_Q:
+      return h->Q;
+  }
+  return nullptr;
+}
+
+struct PhaseTimer
+{
+  e2d_handle * h;
+  int          slot;
+  PhaseTimer(e2d_handle * hh, int s)
+    : h(hh)
+    , slot(s)
+  {
+    if (h->timing)
+      cudaEventRecord(h->ev_t[slot][0], h->stream);
+  }
+  ~PhaseTimer()
+  {
+    if (h->timing)
+    { // like the reference's CudaTimer::stop (src/CudaTimer.h:54-62): record + synchronize
+      cudaEventRecord(h->ev_t[slot][1], h->stream);
+      cudaEventSynchronize(h->ev_t[slot][1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev_t[slot][0], h->ev_t[slot][1]);
+      h->timers[slot] += ms * 1e-3;
+    }
+  }
+};
+
+int
+ensure_scratch(e2d_handle * h, int impl)
+{
+  const size_t bytes = h->n * sizeof(double);
+  if ((impl == 0 || impl == 1) && !h->Q)
+  {
+    E2D_CUDA(cudaMalloc(&h->Q, bytes));
+    E2D_CUDA(cudaMemsetAsync(h->Q, 0, bytes, h->stream));
+  }
+  if ((impl == 0 || impl == 1) && !h->Fx)
+  {
+    E2D_CUDA(cudaMalloc(&h->Fx, bytes));
+    E2D_CUDA(cudaMemsetAsync(h->Fx, 0, bytes, h->stream));
+  }
+  if (impl == 0 && !h->Fy)
+  {
+    E2D_CUDA(cudaMalloc(&h->Fy, bytes));
+    E2D_CUDA(cudaMemsetAsync(h->Fy, 0, bytes, h->stream));
+  }
+  if (impl == 1 && !h->Sx)
+  {
+    E2D_CUDA(cudaMalloc(&h->Sx, bytes));
+    E2D_CUDA(cudaMalloc(&h->Sy, bytes));
+    E2D_CUDA(cudaMemsetAsync(h->Sx, 0, bytes, h->stream));
+    E2D_CUDA(cudaMemsetAsync(h->Sy, 0, bytes, h->stream));
+  }
+  return E2D_OK;
+}
+
+// godunov_unsplit_impl (src/HydroRun.h:281-364)
+int
+godunov_impl(e2d_handle * h, double * in, double * out, double dt, bool do_bc)
+{
+  const e2d_params & p = h->p;
+  const double       dtdx = dt / p.dx; // :290-291
+  const double       dtdy = dt / p.dy;
+  cudaStream_t       st = h->stream;
+
+  if (do_bc)
+  {
+    PhaseTimer tb(h, 0);
+    E2D_CUDA(launch_make_boundaries(p, h->g, in, faces_for(h), nullptr, st)); // :296
+  }
+  const int impl = p.implementationVersion;
+  if (int rc = ensure_scratch(h, impl))
+    return rc;
+
+  PhaseTimer tg(h, 1);
+  if (impl == 2)
+  {
+    // fused: no deep_copy, no Q array (the reference's impl 2 keeps both, :302,:309,:359)
+    E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, nullptr, nullptr, st));
+    return E2D_OK;
+  }
+  E2D_CUDA(cudaMemcpyAsync(out, in, h->n * sizeof(double), cudaMemcpyDeviceToDevice, st)); // :302
+  {
+    PhaseTimer tp(h, 2);
+    E2D_CUDA(launch_convert_to_primitives(p, h->g, in, h->Q, st)); // :309
+  }
+  if (impl == 0)
+  {
+    {
+      PhaseTimer tf(h, 3);
+      E2D_CUDA(launch_compute_and_store_fluxes(p, h->g, h->Q, h->Fx, h->Fy, dtdx, dtdy, st)); // :319
+    }
+    {
+      PhaseTimer tu(h, 4);
+      E2D_CUDA(launch_update(p, h->g, out, h->Fx, h->Fy, st)); // :326
+    }
+  }
+  else
+  { // :338-352
+    E2D_CUDA(launch_compute_slopes(p, h->g, h->Q, h->Sx, h->Sy, st));
+    E2D_CUDA(launch_trace_and_fluxes(p, h->g, h->Q, h->Sx, h->Sy, h->Fx, dtdx, dtdy, 1, st));
+    E2D_CUDA(launch_update_dir(p, h->g, out, h->Fx, 1, st));
+    E2D_CUDA(launch_trace_and_fluxes(p, h->g, h->Q, h->Sx, h->Sy, h->Fx, dtdx, dtdy, 2, st));
+    E2D_CUDA(launch_update_dir(p, h->g, out, h->Fx, 2, st));
+  }
+  return E2D_OK;
+}
+
+void
+soa_from_kokkos_omp(const double * src, double * dst, int isize, int jsize)
+{
+  for (int v = 0; v < 4; ++v)
+    for (int j = 0; j < jsize; ++j)
+      for (int i = 0; i < isize; ++i)
+        dst[(size_t)i + (size_t)isize * ((size_t)j + (size_t)jsize * v)] = src[((size_t)i * jsize + j) * 4 + v];
+}
+
+void
+soa_to_kokkos_omp(const double * src, double * dst, int isize, int jsize)
+{
+  for (int v = 0; v < 4; ++v)
+    for (int j = 0; j < jsize; ++j)
+      for (int i = 0; i < isize; ++i)
+        dst[((size_t)i * jsize + j) * 4 + v] = src[(size_t)i + (size_t)isize * ((size_t)j + (size_t)jsize * v)];
+}
+
+int
+check_slab_args(const e2d_params * p, int jsize_loc)
+{
+  if (!p)
+    return fail(E2D_ERR_INVALID, "params is NULL");
+  // nx, ny >= 2: with a single interior cell the reference's boundary passes read ghost cells written by
+  // an earlier pass (src/HydroRunFunctors.h:1895,1933), which the single-launch fill does not reproduce
+  if (p->nx < 2 || p->isize != p->nx + 4 || jsize_loc < 6 || p->ghostWidth != 2)
+    return fail(E2D_ERR_INVALID, "inconsistent geometry (need nx>=2, isize=nx+4, jsize_loc>=6, ghostWidth=2)");
+  return E2D_OK;
+}
+
+} // namespace
+
+// ==========================================================================================
+extern "C"
+{
+
+  const char *
+  e2d_version(void)
+  {
+    return "euler2d_b200 0.1 (sm_100a, strict fp64)";
+  }
+
+  const char *
+  e2d_status_string(int status)
+  {
+    switch (status)
+    {
+      case E2D_OK:
+        return "ok";
+      case E2D_ERR_INVALID:
+        return "invalid argument";
+      case E2D_ERR_IO:
+        return "i/o error";
+      case E2D_ERR_CUDA:
+        return "CUDA error";
+      case E2D_ERR_ALLOC:
+        return "allocation failed";
+      case E2D_ERR_UNSUPPORTED:
+        return "unsupported";
+    }
+    return "unknown status";
+  }
+
+  const char *
+  e2d_last_error(void)
+  {
+    return g_last_error.c_str();
+  }
+
+  int
+  e2d_device_count(void)
+  {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return 0;
+    }
+    return n;
+  }
+
+  unsigned long long
+  e2d_kernel_launch_count(void)
+  {
+    return g_launches.load();
+  }
+
+  // ---------------------------------------------------------------- kernel-level entry points
+  int
+  e2d_k_init_problem(const e2d_params * p, double * U, int jsize_loc, int j_off, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    if (p->problemType == E2D_PROBLEM_BLAST && p->blast_total_energy_inside > 0 &&
+        (jsize_loc != p->jsize || j_off != 0))
+      return fail(E2D_ERR_UNSUPPORTED, "energy-renormalised blast init needs the whole domain on one device");
+    E2D_CUDA(launch_init_problem(*p, make_geom(*p, jsize_loc, j_off), U, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_make_boundaries(const e2d_params * p, double * U, int jsize_loc, int faces, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    E2D_CUDA(launch_make_boundaries(*p, make_geom(*p, jsize_loc, 0), U, faces, nullptr, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_reduce_invdt(const e2d_params * p, const double * U, int jsize_loc, double * d_invdt, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    E2D_CUDA(launch_reduce_invdt(*p, make_geom(*p, jsize_loc, 0), U, reinterpret_cast<unsigned long long *>(d_invdt),
+                                 (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_convert_to_primitives(const e2d_params * p, const double * U, double * Q, int jsize_loc, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    E2D_CUDA(launch_convert_to_primitives(*p, make_geom(*p, jsize_loc, 0), U, Q, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_compute_and_store_fluxes(const e2d_params * p, const double * Q, double * Fx, double * Fy, double dtdx,
+                                 double dtdy, int jsize_loc, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    E2D_CUDA(launch_compute_and_store_fluxes(*p, make_geom(*p, jsize_loc, 0), Q, Fx, Fy, dtdx, dtdy,
+                                             (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_update(const e2d_params * p, double * U, const double * Fx, const double * Fy, int jsize_loc, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    E2D_CUDA(launch_update(*p, make_geom(*p, jsize_loc, 0), U, Fx, Fy, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_compute_slopes(const e2d_params * p, const double * Q, double * Sx, double * Sy, int jsize_loc,
+                       void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    E2D_CUDA(launch_compute_slopes(*p, make_geom(*p, jsize_loc, 0), Q, Sx, Sy, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_compute_trace_and_fluxes(const e2d_params * p, const double * Q, const double * Sx, const double * Sy,
+                                 double * F, double dtdx, double dtdy, int dir, int jsize_loc, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    if (dir != 1 && dir != 2)
+      return fail(E2D_ERR_INVALID, "dir must be 1 (XDIR) or 2 (YDIR)");
+    E2D_CUDA(launch_trace_and_fluxes(*p, make_geom(*p, jsize_loc, 0), Q, Sx, Sy, F, dtdx, dtdy, dir,
+                                     (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_update_dir(const e2d_params * p, double * U, const double * F, int dir, int jsize_loc, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    if (dir != 1 && dir != 2)
+      return fail(E2D_ERR_INVALID, "dir must be 1 (XDIR) or 2 (YDIR)");
+    E2D_CUDA(launch_update_dir(*p, make_geom(*p, jsize_loc, 0), U, F, dir, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_fused_step(const e2d_params * p, const double * Uin, double * Uout, int jsize_loc, double dt,
+                   const double * d_dt, double * d_invdt, void * stream)
+  {
+    if (int rc = check_slab_args(p, jsize_loc))
+      return rc;
+    if (Uin == Uout)
+      return fail(E2D_ERR_INVALID, "the fused step is out of place: Uin and Uout must differ");
+    E2D_CUDA(launch_fused_step(*p, make_geom(*p, jsize_loc, 0), Uin, Uout, dt, d_dt,
+                               reinterpret_cast<unsigned long long *>(d_invdt), nullptr, (cudaStream_t)stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_k_eval_host(const e2d_params * p, const char * func, const double * in, double * out, long n)
+  {
+    if (!p || !func || !in || !out || n < 0)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    static const struct
+    {
+      const char * name;
+      int          id, nin, nout;
+    } table[] = { { "prim", 0, 4, 5 },   { "slope", 1, 20, 8 }, { "trace", 2, 14, 16 }, { "hllc", 3, 8, 4 },
+                  { "approx", 4, 8, 8 }, { "cmpflx", 5, 4, 4 }, { "hll", 6, 8, 4 } };
+    int id = -1, nin = 0, nout = 0;
+    for (const auto & e : table)
+      if (!std::strcmp(e.name, func))
+        id = e.id, nin = e.nin, nout = e.nout;
+    if (id < 0)
+      return fail(E2D_ERR_INVALID, std::string("unknown function ") + func);
+    if (n == 0)
+      return E2D_OK;
+    double *d_in = nullptr, *d_out = nullptr;
+    E2D_CUDA(cudaMalloc(&d_in, sizeof(double) * nin * n));
+    E2D_CUDA(cudaMalloc(&d_out, sizeof(double) * nout * n));
+    E2D_CUDA(cudaMemcpy(d_in, in, sizeof(double) * nin * n, cudaMemcpyHostToDevice));
+    cudaError_t e = launch_eval(*p, id, d_in, d_out, n, nullptr);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(out, d_out, sizeof(double) * nout * n, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess)
+      return fail_cuda(e, "e2d_k_eval_host");
+    return E2D_OK;
+  }
+
+  // ---------------------------------------------------------------- HydroRun handle
+  int
+  e2d_create(const e2d_params * p, const e2d_slab * slab, double * U_ext, double * U2_ext, void * stream,
+             e2d_handle ** out)
+  {
+    if (!p || !out)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (e2d_device_count() < 1)
+      return fail(E2D_ERR_CUDA, "no CUDA device: euler2d_b200 has no CPU fallback");
+    e2d_handle * h = new (std::nothrow) e2d_handle();
+    if (!h)
+      return fail(E2D_ERR_ALLOC, "out of host memory");
+    h->p = *p;
+    if (slab)
+    {
+      h->slab = *slab;
+      h->whole = (slab->nranks == 1);
+    }
+    else
+    {
+      h->slab.rank = 0;
+      h->slab.nranks = 1;
+      h->slab.ny_loc = p->ny;
+      h->slab.j_off = 0;
+      h->whole = true;
+    }
+    const int jsize_loc = h->slab.ny_loc + 2 * p->ghostWidth;
+    if (int rc = check_slab_args(p, jsize_loc))
+    {
+      delete h;
+      return rc;
+    }
+    h->g = make_geom(*p, jsize_loc, h->slab.j_off);
+    h->n = (size_t)p->isize * jsize_loc * 4;
+    int rc = E2D_OK;
+    do
+    {
+#define E2D_TRY(call)                        \
+  {                                          \
+    cudaError_t e_ = (call);                 \
+    if (e_ != cudaSuccess)                   \
+    {                                        \
+      rc = fail_cuda(e_, #call);             \
+      break;                                 \
+    }                                        \
+  }
+      if (stream)
+        h->stream = (cudaStream_t)stream;
+      else
+      {
+        E2D_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+      }
+      if (U_ext)
+        h->U = U_ext;
+      else
+      {
+        E2D_TRY(cudaMalloc(&h->U, h->n * sizeof(double)));
+        h->own_U = true;
+      }
+      if (U2_ext)
+        h->U2 = U2_ext;
+      else
+      {
+        E2D_TRY(cudaMalloc(&h->U2, h->n * sizeof(double)));
+        h->own_U2 = true;
+      }
+      E2D_TRY(cudaMalloc(&h->d_bits, sizeof(unsigned long long)));
+      E2D_TRY(cudaMalloc(&h->d_loop, sizeof(LoopState)));
+      E2D_TRY(cudaMallocHost(&h->h_loop, sizeof(LoopState)));
+      E2D_TRY(cudaEventCreate(&h->ev[0]));
+      E2D_TRY(cudaEventCreate(&h->ev[1]));
+      for (int k = 0; k < 5 && rc == E2D_OK; ++k)
+        for (int e = 0; e < 2; ++e)
+          if (cudaEventCreate(&h->ev_t[k][e]) != cudaSuccess)
+            rc = fail(E2D_ERR_CUDA, "cudaEventCreate");
+      if (rc != E2D_OK)
+        break;
+      // HydroRun.h:185-214: initial condition, then U2 = U
+      if (p->problemType == E2D_PROBLEM_BLAST && p->blast_total_energy_inside > 0 && !h->whole)
+      {
+        rc = fail(E2D_ERR_UNSUPPORTED, "energy-renormalised blast init needs the whole domain on one device");
+        break;
+      }
+      E2D_TRY(launch_init_problem(*p, h->g, h->U, h->stream));
+      E2D_TRY(cudaMemcpyAsync(h->U2, h->U, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      E2D_TRY(cudaStreamSynchronize(h->stream));
+#undef E2D_TRY
+    } while (0);
+    if (rc != E2D_OK)
+    {
+      e2d_destroy(h);
+      return rc;
+    }
+    *out = h;
+    return E2D_OK;
+  }
+
+  int
+  e2d_destroy(e2d_handle * h)
+  {
+    if (!h)
+      return E2D_OK;
+    if (h->stream)
+      cudaStreamSynchronize(h->stream);
+    if (h->own_U)
+      cudaFree(h->U);
+    if (h->own_U2)
+      cudaFree(h->U2);
+    cudaFree(h->Q);
+    cudaFree(h->Fx);
+    cudaFree(h->Fy);
+    cudaFree(h->Sx);
+    cudaFree(h->Sy);
+    cudaFree(h->d_bits);
+    cudaFree(h->d_loop);
+    cudaFree(h->d_hist);
+    if (h->h_loop)
+      cudaFreeHost(h->h_loop);
+    if (h->ev[0])
+      cudaEventDestroy(h->ev[0]);
+    if (h->ev[1])
+      cudaEventDestroy(h->ev[1]);
+    for (int k = 0; k < 5; ++k)
+      for (int e = 0; e < 2; ++e)
+        if (h->ev_t[k][e])
+          cudaEventDestroy(h->ev_t[k][e]);
+    if (h->own_stream && h->stream)
+      cudaStreamDestroy(h->stream);
+    delete h;
+    return E2D_OK;
+  }
+
+  int
+  e2d_compute_dt(e2d_handle * h, int useU, double * dt, double * invdt_local)
+  {
+    if (!h || !dt)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    const double * A = (useU == 0) ? h->U : h->U2; // HydroRun.h:237-240
+    E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), h->stream));
+    E2D_CUDA(launch_reduce_invdt(h->p, h->g, A, h->d_bits, h->stream));
+    double invDt = 0.0;
+    E2D_CUDA(cudaMemcpyAsync(&invDt, h->d_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+    if (invdt_local)
+      *invdt_local = invDt;
+    *dt = h->p.cfl / invDt; // HydroRun.h:246
+    return E2D_OK;
+  }
+
+  int
+  e2d_make_boundaries(e2d_handle * h, int which)
+  {
+    if (!h || (which != E2D_U && which != E2D_U2))
+      return fail(E2D_ERR_INVALID, "bad argument");
+    E2D_CUDA(launch_make_boundaries(h->p, h->g, array_of(h, which), faces_for(h), nullptr, h->stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_godunov_unsplit(e2d_handle * h, int nStep, double dt)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    h->loop_primed = false;
+    if (nStep % 2 == 0) // HydroRun.h:263-270
+      return godunov_impl(h, h->U, h->U2, dt, true);
+    return godunov_impl(h, h->U2, h->U, dt, true);
+  }
+
+  int
+  e2d_godunov_unsplit_nobc(e2d_handle * h, int nStep, double dt)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    h->loop_primed = false;
+    if (nStep % 2 == 0)
+      return godunov_impl(h, h->U, h->U2, dt, false);
+    return godunov_impl(h, h->U2, h->U, dt, false);
+  }
+
+  int
+  e2d_run(e2d_handle * h, long max_steps, e2d_run_stats * stats)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    if (!h->whole)
+      return fail(E2D_ERR_UNSUPPORTED, "e2d_run drives a whole-domain handle; slabs are stepped by the caller");
+    const e2d_params & p = h->p;
+    cudaStream_t       st = h->stream;
+    if (max_steps < 0)
+      max_steps = p.nStepmax;
+    const unsigned long long launches0 = g_launches.load();
+
+    // dt history buffer
+    if (h->hist_cap < max_steps + 1)
+    {
+      double * nh = nullptr;
+      long     cap = max_steps + 64;
+      E2D_CUDA(cudaMalloc(&nh, sizeof(double) * cap));
+      E2D_CUDA(cudaMemsetAsync(nh, 0, sizeof(double) * cap, st));
+      if (h->d_hist)
+      {
+        E2D_CUDA(cudaMemcpyAsync(nh, h->d_hist, sizeof(double) * h->hist_cap, cudaMemcpyDeviceToDevice, st));
+        E2D_CUDA(cudaStreamSynchronize(st));
+        cudaFree(h->d_hist);
+      }
+      h->d_hist = nh;
+      h->hist_cap = cap;
+    }
+
+    // prime the loop state: (t, nStep) from the handle, invDt of the current array (main.cpp:128)
+    h->h_loop->t = h->t;
+    h->h_loop->dt = h->dt_last;
+    h->h_loop->nStep = h->nStep;
+    h->h_loop->done = !(h->t < p.tEnd && h->nStep < max_steps);
+    h->h_loop->invdt_cur = 0;
+    h->h_loop->invdt_next = 0;
+    E2D_CUDA(cudaMemcpyAsync(h->d_loop, h->h_loop, sizeof(LoopState), cudaMemcpyHostToDevice, st));
+    {
+      const double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
+      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, &h->d_loop->invdt_cur, st));
+    }
+
+    E2D_CUDA(cudaEventRecord(h->ev[0], st));
+    int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when kernels no-op
+    const int batch = 64;
+    bool      finished = h->h_loop->done != 0;
+    while (!finished)
+    {
+      long todo = max_steps - n_host;
+      if (todo > batch)
+        todo = batch;
+      for (long k = 0; k < todo; ++k, ++n_host)
+      {
+        double * in = (n_host % 2 == 0) ? h->U : h->U2;
+        double * out = (n_host % 2 == 0) ? h->U2 : h->U;
+        E2D_CUDA(launch_loop_begin_step(h->d_loop, p.cfl, p.tEnd, st));
+        E2D_CUDA(launch_make_boundaries(p, h->g, in, E2D_FACES_ALL, &h->d_loop->done, st));
+        E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_loop->dt, &h->d_loop->invdt_next,
+                                   &h->d_loop->done, st));
+        E2D_CUDA(launch_loop_end_step(h->d_loop, p.tEnd, (int)max_steps, h->d_hist, h->hist_cap, st));
+      }
+      E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+      E2D_CUDA(cudaStreamSynchronize(st));
+      finished = h->h_loop->done != 0 || n_host >= max_steps;
+    }
+    E2D_CUDA(cudaEventRecord(h->ev[1], st));
+    E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+    E2D_CUDA(cudaEventSynchronize(h->ev[1]));
+    E2D_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    E2D_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->t = h->h_loop->t;
+    h->nStep = h->h_loop->nStep;
+    h->dt_last = h->h_loop->dt;
+    if (stats)
+    {
+      stats->nStep = h->nStep;
+      stats->t = h->t;
+      stats->dt_last = h->dt_last;
+      stats->seconds = ms * 1e-3;
+      stats->launches = (long long)(g_launches.load() - launches0);
+    }
+    return E2D_OK;
+  }
+
+  int
+  e2d_get_dt_history(e2d_handle * h, double * dts, long n_cap, long * n)
+  {
+    if (!h || !dts || !n)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    long cnt = h->nStep < h->hist_cap ? h->nStep : h->hist_cap;
+    if (cnt > n_cap)
+      cnt = n_cap;
+    if (cnt > 0 && h->d_hist)
+    {
+      E2D_CUDA(cudaMemcpyAsync(dts, h->d_hist, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+      E2D_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    else
+      cnt = 0;
+    *n = cnt;
+    return E2D_OK;
+  }
+
+  int
+  e2d_set_time(e2d_handle * h, double t, int nStep)
+  {
+    if (!h || nStep < 0)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    h->t = t;
+    h->nStep = nStep;
+    return E2D_OK;
+  }
+
+  int
+  e2d_download(e2d_handle * h, int which, double * host, int layout)
+  {
+    double * A = h ? array_of(h, which) : nullptr;
+    if (!A || !host)
+      return fail(E2D_ERR_INVALID, "bad argument (array not allocated?)");
+    if (layout == E2D_LAYOUT_SOA)
+    {
+      E2D_CUDA(cudaMemcpyAsync(host, A, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      E2D_CUDA(cudaStreamSynchronize(h->stream));
+      return E2D_OK;
+    }
+    if (layout != E2D_LAYOUT_KOKKOS_OMP)
+      return fail(E2D_ERR_INVALID, "unknown layout");
+    std::vector<double> tmp(h->n);
+    E2D_CUDA(cudaMemcpyAsync(tmp.data(), A, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+    soa_to_kokkos_omp(tmp.data(), host, h->g.isize, h->g.jsize);
+    return E2D_OK;
+  }
+
+  int
+  e2d_upload(e2d_handle * h, int which, const double * host, int layout)
+  {
+    double * A = h ? array_of(h, which) : nullptr;
+    if (!A || !host)
+      return fail(E2D_ERR_INVALID, "bad argument (array not allocated?)");
+    h->loop_primed = false;
+    if (layout == E2D_LAYOUT_SOA)
+    {
+      E2D_CUDA(cudaMemcpyAsync(A, host, h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      E2D_CUDA(cudaStreamSynchronize(h->stream));
+      return E2D_OK;
+    }
+    if (layout != E2D_LAYOUT_KOKKOS_OMP)
+      return fail(E2D_ERR_INVALID, "unknown layout");
+    std::vector<double> tmp(h->n);
+    soa_from_kokkos_omp(host, tmp.data(), h->g.isize, h->g.jsize);
+    E2D_CUDA(cudaMemcpyAsync(A, tmp.data(), h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+    return E2D_OK;
+  }
+
+  double *
+  e2d_device_ptr(e2d_handle * h, int which)
+  {
+    return h ? array_of(h, which) : nullptr;
+  }
+
+  void *
+  e2d_stream(e2d_handle * h)
+  {
+    return h ? (void *)h->stream : nullptr;
+  }
+
+  int
+  e2d_synchronize(e2d_handle * h)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+    return E2D_OK;
+  }
+
+  int
+  e2d_get_params(e2d_handle * h, e2d_params * out)
+  {
+    if (!h || !out)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    *out = h->p;
+    return E2D_OK;
+  }
+
+  int
+  e2d_step_host(e2d_handle * h, const double * U_host_in, double * U_host_out, double * dt_out)
+  {
+    if (!h || !U_host_in || !U_host_out)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    const e2d_params & p = h->p;
+    cudaStream_t       st = h->stream;
+    const size_t       bytes = h->n * sizeof(double);
+    E2D_CUDA(cudaMemcpyAsync(h->U, U_host_in, bytes, cudaMemcpyHostToDevice, st));
+    E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), st));
+    E2D_CUDA(launch_reduce_invdt(p, h->g, h->U, h->d_bits, st));
+    E2D_CUDA(launch_make_boundaries(p, h->g, h->U, faces_for(h), nullptr, st));
+    // dt = cfl / invDt on the device (IEEE division, same value as HydroRun.h:246), no host round trip
+    h->h_loop->t = 0.0;
+    h->h_loop->dt = 0.0;
+    h->h_loop->nStep = 0;
+    h->h_loop->done = 0;
+    h->h_loop->invdt_cur = 0;
+    h->h_loop->invdt_next = 0;
+    E2D_CUDA(cudaMemcpyAsync(h->d_loop, h->h_loop, sizeof(LoopState), cudaMemcpyHostToDevice, st));
+    E2D_CUDA(cudaMemcpyAsync(&h->d_loop->invdt_cur, h->d_bits, sizeof(unsigned long long),
+                             cudaMemcpyDeviceToDevice, st));
+    E2D_CUDA(launch_loop_begin_step(h->d_loop, p.cfl, 1e300, st));
+    E2D_CUDA(launch_fused_step(p, h->g, h->U, h->U2, 0.0, &h->d_loop->dt, nullptr, nullptr, st));
+    // ghosts of the output: the reference's out array carries the input's filled ghosts (HydroRun.h:302)
+    E2D_CUDA(launch_make_boundaries(p, h->g, h->U2, faces_for(h), nullptr, st));
+    E2D_CUDA(cudaMemcpyAsync(U_host_out, h->U2, bytes, cudaMemcpyDeviceToHost, st));
+    E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+    E2D_CUDA(cudaStreamSynchronize(st));
+    if (dt_out)
+      *dt_out = h->h_loop->dt;
+    h->loop_primed = false;
+    return E2D_OK;
+  }
+
+  int
+  e2d_save_vtk(e2d_handle * h, int which, int iStep)
+  {
+    double * A = h ? array_of(h, which) : nullptr;
+    if (!A)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    const e2d_params &  p = h->p;
+    std::vector<double> host(h->n);
+    E2D_CUDA(cudaMemcpyAsync(host.data(), A, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+
+    // HydroRun.h:537-544
+    std::ostringstream stepNum;
+    stepNum.width(7);
+    stepNum.fill('0');
+    stepNum << iStep;
+    const std::string filename = std::string(p.outputDir) + "/" + p.outputPrefix + "_" + stepNum.str() + ".vti";
+    std::fstream      f;
+    f.open(filename.c_str(), std::ios_base::out);
+    if (!f.is_open())
+      return fail(E2D_ERR_IO, "cannot open " + filename);
+
+    const int isize = h->g.isize, jsize = h->g.jsize, nx = p.nx, ny = h->g.ny;
+    // HydroRun.h:551-570 (little-endian host)
+    f << "<?xml version=\"1.0\"?>\n";
+    f << "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\">\n";
+    f << "  <ImageData WholeExtent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << 0 << "\" "
+      << "Origin=\"" << p.xmin << " " << p.ymin << " " << 0.0 << "\" "
+      << "Spacing=\"" << p.dx << " " << p.dy << " " << 0.0 << "\">\n";
+    f << "  <Piece Extent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << 0 << " "
+      << "\">\n";
+    f << "    <PointData>\n";
+    f << "    </PointData>\n";
+    f << "    <CellData>\n";
+    static const char * varNames[4] = { "rho", "E", "mx", "my" }; // HydroParams.cpp:17
+    for (int v = 0; v < 4; ++v)
+    { // HydroRun.h:573-598: interior cells, i fastest
+      f << "    <DataArray type=\"Float64\" Name=\"" << varNames[v] << "\" format=\"ascii\" >\n";
+      for (int j = 2; j < jsize - 2; ++j)
+        for (int i = 2; i < isize - 2; ++i)
+          f << host[(size_t)i + (size_t)isize * ((size_t)j + (size_t)jsize * v)] << " ";
+      f << "\n    </DataArray>\n";
+    }
+    f << "    </CellData>\n";
+    f << "  </Piece>\n";
+    f << "  </ImageData>\n";
+    f << "</VTKFile>\n";
+    f.close();
+    return f.fail() ? fail(E2D_ERR_IO, "write failed: " + filename) : (int)E2D_OK;
+  }
+
+  int
+  e2d_enable_timers(e2d_handle * h, int on)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    h->timing = on != 0;
+    return E2D_OK;
+  }
+
+  int
+  e2d_get_timers(e2d_handle * h, double out[5])
+  {
+    if (!h || !out)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    // boundaries, godunov, primitive, fluxes, update  (HydroRun.h:74-75)
+    for (int k = 0; k < 5; ++k)
+      out[k] = h->timers[k];
+    return E2D_OK;
+  }
+
+} // extern "C"

@@ -1,0 +1,69 @@
+// Internal C++ interface between the C ABI (e2d_capi.cu) and the kernels (e2d_kernels.cu).
+#ifndef E2D_INTERNAL_H
+#define E2D_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include "../../include/euler2d_b200.h"
+#include "e2d_math.cuh"
+
+namespace e2d
+{
+
+// geometry of one slab as the kernels see it
+struct Geom
+{
+  int isize, jsize; // extent incl. ghosts (jsize = local rows)
+  int nx, ny;       // interior extent (ny = local interior rows)
+  int j_off;        // global row of local row 0
+};
+
+// device-resident time-loop state (src/main.cpp:61-62,100-143 keeps these on the host)
+struct LoopState
+{
+  double             t;
+  double             dt;
+  unsigned long long invdt_cur;  // bit pattern of max invDt of the current state
+  unsigned long long invdt_next; // accumulated by the step kernel for the state it writes
+  int                nStep;
+  int                done;
+};
+
+Settings make_settings(const e2d_params & p);
+Geom     make_geom(const e2d_params & p, int jsize_loc, int j_off);
+
+// every launcher returns cudaGetLastError() after the launch
+cudaError_t launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream_t st);
+cudaError_t launch_make_boundaries(const e2d_params & p, const Geom & g, double * U, int faces, const int * d_done,
+                                   cudaStream_t st);
+cudaError_t launch_reduce_invdt(const e2d_params & p, const Geom & g, const double * U, unsigned long long * d_bits,
+                                cudaStream_t st);
+cudaError_t launch_convert_to_primitives(const e2d_params & p, const Geom & g, const double * U, double * Q,
+                                         cudaStream_t st);
+cudaError_t launch_compute_and_store_fluxes(const e2d_params & p, const Geom & g, const double * Q, double * Fx,
+                                            double * Fy, double dtdx, double dtdy, cudaStream_t st);
+cudaError_t launch_update(const e2d_params & p, const Geom & g, double * U, const double * Fx, const double * Fy,
+                          cudaStream_t st);
+cudaError_t launch_compute_slopes(const e2d_params & p, const Geom & g, const double * Q, double * Sx, double * Sy,
+                                  cudaStream_t st);
+cudaError_t launch_trace_and_fluxes(const e2d_params & p, const Geom & g, const double * Q, const double * Sx,
+                                    const double * Sy, double * F, double dtdx, double dtdy, int dir,
+                                    cudaStream_t st);
+cudaError_t launch_update_dir(const e2d_params & p, const Geom & g, double * U, const double * F, int dir,
+                              cudaStream_t st);
+cudaError_t launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
+                              const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done,
+                              cudaStream_t st);
+// scalar bookkeeping of the device-resident loop
+cudaError_t launch_loop_begin_step(LoopState * st_dev, double cfl, double tEnd, cudaStream_t st);
+cudaError_t launch_loop_end_step(LoopState * st_dev, double tEnd, int max_steps, double * dt_hist, long hist_cap,
+                                 cudaStream_t st);
+cudaError_t launch_eval(const e2d_params & p, int func, const double * d_in, double * d_out, long n,
+                        cudaStream_t st);
+
+int  solver_for(const e2d_params & p); // 2 (HLLC) unless honourRiemannSolver
+void count_launch(int n = 1);
+
+} // namespace e2d
+
+#endif

@@ -1,0 +1,954 @@
+// sm_100a kernels of the unsplit MUSCL-Hancock Godunov step.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (strict: bit parity with the
+// reference's FMA-free x86 build).  Data layout: SoA planes, off = i + isize*(j + jsize*var);
+// threadIdx.x always walks i, so every global access of a warp is a contiguous 256-byte run.
+#include <cstdio>
+
+#include "e2d_internal.h"
+#include "e2d_march.cuh"
+
+namespace e2d
+{
+
+namespace
+{
+
+constexpr int kBX = 128;       // threads per block of the marching kernel (= columns incl. 4 halo columns)
+constexpr int kMarchMinBlocks = 3;
+
+__host__ __device__ __forceinline__ size_t
+cell(const Geom & g, int i, int j, int v)
+{
+  return (size_t)i + (size_t)g.isize * ((size_t)j + (size_t)g.jsize * (size_t)v);
+}
+
+__device__ __forceinline__ void
+load4(const double * __restrict__ A, const Geom & g, int i, int j, double q[4])
+{
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const size_t o = (size_t)i + (size_t)g.isize * j;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    q[v] = A[o + v * plane];
+}
+
+__device__ __forceinline__ void
+store4(double * __restrict__ A, const Geom & g, int i, int j, const double q[4])
+{
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const size_t o = (size_t)i + (size_t)g.isize * j;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    A[o + v * plane] = q[v];
+}
+
+// ------------------------------------------------------------------------------------------
+// Problem initialisers: Init*Functor, src/HydroRunFunctors.h:1347-1827.
+// Cell centre  x = xmin + dx/2 + (i - ghostWidth)*dx  (:1384-1385) with the GLOBAL row index.
+// ------------------------------------------------------------------------------------------
+struct InitArgs
+{
+  int    problem;
+  double xmin, ymin, dx, dy, gamma0;
+  double blast_radius, blast_center_x, blast_center_y, blast_density_in, blast_density_out;
+  double blast_pressure_in, blast_pressure_out;
+  double blast_energy_density; // total_energy_inside / volume_inside, or < 0 when not used
+  double bubble_radius, bubble_center_x, bubble_center_y, bubble_density, bubble_pressure;
+  double preshock_density, preshock_pressure, postshock_density, postshock_pressure, postshock_velocity;
+  double shock_loc;
+};
+
+__global__ void __launch_bounds__(128)
+k_init_problem(Geom g, InitArgs a, double * __restrict__ U, unsigned long long * __restrict__ n_inside)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= g.isize || j >= g.jsize)
+    return;
+  const int    gw = 2;
+  const double x = a.xmin + a.dx / 2 + (i - gw) * a.dx;
+  const double y = a.ymin + a.dy / 2 + (j + g.j_off - gw) * a.dy;
+  double       u[4] = { 0.0, 0.0, 0.0, 0.0 };
+
+  if (a.problem == E2D_PROBLEM_BLAST)
+  { // :1466-1545
+    const double radius2 = a.blast_radius * a.blast_radius;
+    const double d2 = (x - a.blast_center_x) * (x - a.blast_center_x) +
+                      (y - a.blast_center_y) * (y - a.blast_center_y);
+    if (d2 < radius2)
+    {
+      u[ID] = a.blast_density_in;
+      u[IP] = a.blast_pressure_in / (a.gamma0 - 1.0);
+      if (n_inside)
+        atomicAdd(n_inside, 1ull);
+      if (a.blast_energy_density >= 0.0)
+        u[IP] = a.blast_energy_density;
+    }
+    else
+    {
+      u[ID] = a.blast_density_out;
+      u[IP] = a.blast_pressure_out / (a.gamma0 - 1.0);
+    }
+  }
+  else if (a.problem == E2D_PROBLEM_FOUR_QUADRANT)
+  { // :1578-1665, Lax-Liu configuration 3 split at (0.8, 0.8)
+    const double xt = 0.8, yt = 0.8;
+    double       rho, p, vx, vy;
+    if (x < xt)
+    {
+      if (y < yt)
+      {
+        rho = 0.138, p = 0.029, vx = 1.206, vy = 1.206;
+      }
+      else
+      {
+        rho = 0.5323, p = 0.3, vx = 1.206, vy = 0.0;
+      }
+    }
+    else
+    {
+      if (y < yt)
+      {
+        rho = 0.5323, p = 0.3, vx = 0.0, vy = 1.206;
+      }
+      else
+      {
+        rho = 1.5, p = 1.5, vx = 0.0, vy = 0.0;
+      }
+    }
+    u[ID] = rho; // primToCons :1578-1591
+    u[IU] = vx * rho;
+    u[IV] = vy * rho;
+    u[IP] = p / (a.gamma0 - 1.0) + rho * (vx * vx + vy * vy) * 0.5;
+  }
+  else if (a.problem == E2D_PROBLEM_DISCONTINUITY)
+  { // :1713-1729
+    u[ID] = (x + y < 1) ? 1.0 + x * x : 0.25;
+    u[IP] = 1.0 / (a.gamma0 - 1.0);
+  }
+  else if (a.problem == E2D_PROBLEM_SHOCKED_BUBBLE)
+  { // :1776-1820
+    double pres;
+    if (x < a.shock_loc)
+    {
+      u[ID] = a.postshock_density;
+      u[IU] = a.postshock_density * a.postshock_velocity;
+      pres = a.postshock_pressure;
+    }
+    else
+    {
+      const double radius = sqrt((x - a.bubble_center_x) * (x - a.bubble_center_x) +
+                                 (y - a.bubble_center_y) * (y - a.bubble_center_y));
+      if (radius < a.bubble_radius)
+      {
+        u[ID] = a.bubble_density;
+        pres = a.bubble_pressure;
+      }
+      else
+      {
+        u[ID] = a.preshock_density;
+        pres = a.preshock_pressure;
+      }
+    }
+    const double rho_eint = pres / (a.gamma0 - 1);
+    u[IE] = rho_eint + 0.5 * (u[IU] * u[IU] + u[IV] * u[IV]) / u[ID];
+  }
+  else
+  { // implode :1384-1401 (also the reference's fallback for an unknown problem, HydroRun.h:205-211)
+    const double tmp = x + y * y;
+    if (tmp > 0.5 && tmp < 1.5)
+    {
+      u[ID] = 1.0;
+      u[IP] = 1.0 / (a.gamma0 - 1.0);
+    }
+    else
+    {
+      u[ID] = 0.125;
+      u[IP] = 0.14 / (a.gamma0 - 1.0);
+    }
+  }
+  store4(U, g, i, j, u);
+}
+
+// ------------------------------------------------------------------------------------------
+// Boundary fill: the four MakeBoundariesFunctor<face> launches of HydroRun::make_boundaries
+// (src/HydroRunFunctors.h:1832-2030, src/HydroRun.h:390-399) as ONE launch.
+//
+// The reference runs XMIN, XMAX over all rows and then YMIN, YMAX over all columns, so a corner
+// ghost ends up as  (U(i0, j0) * sign_x) * sign_y.  Every source cell (i0, j0) is an interior cell,
+// which no pass writes, so each ghost cell can be produced independently by composing the two
+// index maps — same values, same signs (multiplying by +-1.0 is exact), no ordering between threads.
+// ------------------------------------------------------------------------------------------
+struct BcArgs
+{
+  int bc_xmin, bc_xmax, bc_ymin, bc_ymax;
+  int faces;
+};
+
+__device__ __forceinline__ int
+bc_source_lo(int bc, int k, int n, double & sign, bool is_normal)
+{ // ghost index k in {0,1}; :1893-1906 / :1968-1981
+  if (bc == E2D_BC_DIRICHLET)
+  {
+    if (is_normal)
+      sign = -1.0;
+    return 3 - k;
+  }
+  if (bc == E2D_BC_NEUMANN)
+    return 2;
+  return n + k; // periodic
+}
+
+__device__ __forceinline__ int
+bc_source_hi(int bc, int k, int n, double & sign, bool is_normal)
+{ // ghost index k in {n+2, n+3}; :1931-1944 / :2006-2019
+  if (bc == E2D_BC_DIRICHLET)
+  {
+    if (is_normal)
+      sign = -1.0;
+    return 2 * n + 3 - k;
+  }
+  if (bc == E2D_BC_NEUMANN)
+    return n + 1;
+  return k - n; // periodic
+}
+
+__global__ void __launch_bounds__(128)
+k_make_boundaries(Geom g, BcArgs a, double * __restrict__ U, const int * __restrict__ d_done)
+{
+  if (d_done && *d_done)
+    return;
+  const int    nx = g.nx, ny = g.ny;
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const int    k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int    n_y = 4 * g.isize; // y-ghost rows, full width (i fastest)
+  const int    n_x = 4 * g.jsize; // x-ghost columns
+
+  int  i, j;
+  bool in_x_ghost, in_y_ghost;
+  if (k < n_y)
+  {
+    const int gsel = k / g.isize;
+    i = k - gsel * g.isize;
+    j = gsel < 2 ? gsel : ny + gsel;
+    if (!(a.faces & (gsel < 2 ? E2D_FACES_YMIN : E2D_FACES_YMAX)))
+      return;
+  }
+  else if (k < n_y + n_x)
+  {
+    const int kk = k - n_y;
+    j = kk >> 2;
+    const int gsel = kk & 3;
+    i = gsel < 2 ? gsel : nx + gsel;
+    if (!(a.faces & (gsel < 2 ? 1 : 2)))
+      return;
+    // rows that an active y face rewrites are produced by the first branch
+    if ((j < 2 && (a.faces & E2D_FACES_YMIN)) || (j >= ny + 2 && (a.faces & E2D_FACES_YMAX)))
+      return;
+  }
+  else
+    return;
+
+  in_x_ghost = (i < 2 && (a.faces & 1)) || (i >= nx + 2 && (a.faces & 2));
+  in_y_ghost = (j < 2 && (a.faces & E2D_FACES_YMIN)) || (j >= ny + 2 && (a.faces & E2D_FACES_YMAX));
+
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+  {
+    double sx = 1.0, sy = 1.0;
+    int    i0 = i, j0 = j;
+    if (in_x_ghost)
+      i0 = (i < 2) ? bc_source_lo(a.bc_xmin, i, nx, sx, v == IU) : bc_source_hi(a.bc_xmax, i, nx, sx, v == IU);
+    if (in_y_ghost)
+      j0 = (j < 2) ? bc_source_lo(a.bc_ymin, j, ny, sy, v == IV) : bc_source_hi(a.bc_ymax, j, ny, sy, v == IV);
+    double val = U[(size_t)i0 + (size_t)g.isize * j0 + v * plane];
+    if (in_x_ghost)
+      val = val * sx;
+    if (in_y_ghost)
+      val = val * sy;
+    U[(size_t)i + (size_t)g.isize * j + v * plane] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CFL reduction: ComputeDtFunctor, src/HydroRunFunctors.h:17-79.
+// max is exact and order independent, so any reduction tree reproduces the reference's value.
+// invDt is non-negative, so its IEEE bit pattern orders like an unsigned integer: the cross-block
+// step is a single atomicMax on 64-bit integers (no CAS loop, no second kernel).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double
+warp_max(double x)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
+__device__ __forceinline__ void
+block_max_to_global(double x, unsigned long long * __restrict__ bits)
+{
+  __shared__ double warp_part[32];
+  const int         lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int         nw = (blockDim.x + 31) >> 5;
+  x = warp_max(x);
+  if (lane == 0)
+    warp_part[w] = x;
+  __syncthreads();
+  if (w == 0)
+  {
+    x = lane < nw ? warp_part[lane] : 0.0;
+    x = warp_max(x);
+    if (lane == 0 && x > 0.0)
+      atomicMax(bits, (unsigned long long)__double_as_longlong(x));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_reduce_invdt(Geom g, Settings s, const double * __restrict__ U, unsigned long long * __restrict__ bits)
+{
+  const size_t plane = (size_t)g.isize * g.jsize;
+  double       m = 0.0;
+  for (int j = 2 + blockIdx.y; j < g.jsize - 2; j += gridDim.y)
+    for (int i = 2 + blockIdx.x * blockDim.x + threadIdx.x; i < g.isize - 2; i += gridDim.x * blockDim.x)
+    {
+      const size_t o = (size_t)i + (size_t)g.isize * j;
+      const double v = cfl_inv_dt(s, U[o], U[o + plane], U[o + 2 * plane], U[o + 3 * plane]);
+      m = fmax(m, v); // fmax drops a NaN operand, like the reference's fmax(invDt, ...) at :72
+    }
+  block_max_to_global(m, bits);
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvertToPrimitivesFunctor, src/HydroRunFunctors.h:84-143 (whole array incl. ghosts)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_convert_to_primitives(Geom g, Settings s, const double * __restrict__ U, double * __restrict__ Q)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= g.isize)
+    return;
+  double u[4], q[4];
+  load4(U, g, i, j, u);
+  compute_primitives_noc(s, u[ID], u[IP], u[IU], u[IV], q[ID], q[IP], q[IU], q[IV]);
+  store4(Q, g, i, j, q);
+}
+
+// ------------------------------------------------------------------------------------------
+// ComputeAndStoreFluxesFunctor, src/HydroRunFunctors.h:412-651 — the unfused flux kernel of
+// implementation 0: thread (i,j) produces the flux through its west and south faces.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void
+cell_slopes(const Settings & s, const Geom & g, const double * __restrict__ Q, int i, int j, double q[4],
+            double dqX[4], double dqY[4])
+{
+  double qp[4], qm[4];
+  load4(Q, g, i, j, q);
+  load4(Q, g, i + 1, j, qp);
+  load4(Q, g, i - 1, j, qm);
+  slopes_dir(s, q, qp, qm, dqX);
+  load4(Q, g, i, j + 1, qp);
+  load4(Q, g, i, j - 1, qm);
+  slopes_dir(s, q, qp, qm, dqY);
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(128)
+k_compute_and_store_fluxes(Geom g, Settings s, const double * __restrict__ Q, double * __restrict__ Fx,
+                           double * __restrict__ Fy, double dtdx, double dtdy)
+{
+  const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 2 + blockIdx.y;
+  if (i > g.isize - 2 || j > g.jsize - 2)
+    return;
+  double q[4], dqX[4], dqY[4], s0[4], qn[4], dqXn[4], dqYn[4], s0n[4], ql[4], qr[4], f[4];
+  double f_d, f_e, f_n, f_t;
+
+  cell_slopes(s, g, Q, i, j, q, dqX, dqY);
+  trace_sources(s, q, dqX, dqY, s0);
+
+  // west face (:519-575)
+  cell_slopes(s, g, Q, i - 1, j, qn, dqXn, dqYn);
+  trace_sources(s, qn, dqXn, dqYn, s0n);
+  trace_face<-1>(s, q, dqX, s0, dtdx, qr);
+  trace_face<+1>(s, qn, dqXn, s0n, dtdx, ql);
+  riemann<SOLVER>(s, ql[ID], ql[IP], ql[IU], ql[IV], qr[ID], qr[IP], qr[IU], qr[IV], f_d, f_e, f_n, f_t);
+  f[ID] = f_d * dtdx;
+  f[IP] = f_e * dtdx;
+  f[IU] = f_n * dtdx;
+  f[IV] = f_t * dtdx;
+  store4(Fx, g, i, j, f);
+
+  // south face (:581-640), IU<->IV swapped around the solve
+  cell_slopes(s, g, Q, i, j - 1, qn, dqXn, dqYn);
+  trace_sources(s, qn, dqXn, dqYn, s0n);
+  trace_face<-1>(s, q, dqY, s0, dtdy, qr);
+  trace_face<+1>(s, qn, dqYn, s0n, dtdy, ql);
+  riemann<SOLVER>(s, ql[ID], ql[IP], ql[IV], ql[IU], qr[ID], qr[IP], qr[IV], qr[IU], f_d, f_e, f_n, f_t);
+  f[ID] = f_d * dtdy;
+  f[IP] = f_e * dtdy;
+  f[IU] = f_t * dtdy;
+  f[IV] = f_n * dtdy;
+  store4(Fy, g, i, j, f);
+}
+
+// UpdateFunctor, src/HydroRunFunctors.h:656-723
+__global__ void __launch_bounds__(256)
+k_update(Geom g, double * __restrict__ U, const double * __restrict__ Fx, const double * __restrict__ Fy)
+{
+  const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 2 + blockIdx.y;
+  if (i >= g.isize - 2 || j >= g.jsize - 2)
+    return;
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const size_t o = (size_t)i + (size_t)g.isize * j;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+  {
+    double x = U[o + v * plane];
+    x += Fx[o + v * plane];
+    x -= Fx[o + 1 + v * plane];
+    x += Fy[o + v * plane];
+    x -= Fy[o + g.isize + v * plane];
+    U[o + v * plane] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// implementation 1: ComputeSlopesFunctor :1061-1162, ComputeTraceAndFluxes_Functor<dir> :1167-1342,
+// UpdateDirFunctor<dir> :986-1055
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_compute_slopes(Geom g, Settings s, const double * __restrict__ Q, double * __restrict__ Sx,
+                 double * __restrict__ Sy)
+{
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y;
+  if (i > g.isize - 2 || j > g.jsize - 2)
+    return;
+  double q[4], dqX[4], dqY[4];
+  cell_slopes(s, g, Q, i, j, q, dqX, dqY);
+  store4(Sx, g, i, j, dqX);
+  store4(Sy, g, i, j, dqY);
+}
+
+template <int SOLVER, int DIR>
+__global__ void __launch_bounds__(128)
+k_trace_and_fluxes(Geom g, Settings s, const double * __restrict__ Q, const double * __restrict__ Sx,
+                   const double * __restrict__ Sy, double * __restrict__ F, double dtdx, double dtdy)
+{
+  const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 2 + blockIdx.y;
+  if (i > g.isize - 2 || j > g.jsize - 2)
+    return;
+  const int in = DIR == 1 ? i - 1 : i, jn = DIR == 1 ? j : j - 1;
+  double    q[4], dqX[4], dqY[4], s0[4], ql[4], qr[4], f[4];
+  double    f_d, f_e, f_n, f_t;
+  load4(Q, g, i, j, q);
+  load4(Sx, g, i, j, dqX);
+  load4(Sy, g, i, j, dqY);
+  trace_sources(s, q, dqX, dqY, s0);
+  if (DIR == 1)
+    trace_face<-1>(s, q, dqX, s0, dtdx, qr);
+  else
+    trace_face<-1>(s, q, dqY, s0, dtdy, qr);
+  load4(Q, g, in, jn, q);
+  load4(Sx, g, in, jn, dqX);
+  load4(Sy, g, in, jn, dqY);
+  trace_sources(s, q, dqX, dqY, s0);
+  if (DIR == 1)
+  {
+    trace_face<+1>(s, q, dqX, s0, dtdx, ql);
+    riemann<SOLVER>(s, ql[ID], ql[IP], ql[IU], ql[IV], qr[ID], qr[IP], qr[IU], qr[IV], f_d, f_e, f_n, f_t);
+    f[ID] = f_d * dtdx;
+    f[IP] = f_e * dtdx;
+    f[IU] = f_n * dtdx;
+    f[IV] = f_t * dtdx;
+  }
+  else
+  {
+    trace_face<+1>(s, q, dqY, s0, dtdy, ql);
+    riemann<SOLVER>(s, ql[ID], ql[IP], ql[IV], ql[IU], qr[ID], qr[IP], qr[IV], qr[IU], f_d, f_e, f_n, f_t);
+    f[ID] = f_d * dtdy;
+    f[IP] = f_e * dtdy;
+    f[IU] = f_t * dtdy;
+    f[IV] = f_n * dtdy;
+  }
+  store4(F, g, i, j, f);
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256)
+k_update_dir(Geom g, double * __restrict__ U, const double * __restrict__ F)
+{
+  const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 2 + blockIdx.y;
+  if (i >= g.isize - 2 || j >= g.jsize - 2)
+    return;
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const size_t o = (size_t)i + (size_t)g.isize * j;
+  const size_t on = DIR == 1 ? o + 1 : o + g.isize;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+  {
+    double x = U[o + v * plane];
+    x += F[o + v * plane];
+    x -= F[on + v * plane];
+    U[o + v * plane] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The fused step (e2d_march.cuh)
+// ------------------------------------------------------------------------------------------
+template <int SOLVER, bool FUSE_DT>
+__global__ void __launch_bounds__(kBX, kMarchMinBlocks)
+k_fused_step(MarchArgs a, const int * __restrict__ d_done)
+{
+  if (d_done && *d_done)
+    return;
+  __shared__ MarchSmem<kBX>          sm;
+  MarchThread<kBX, SOLVER, FUSE_DT> th;
+  if (!th.init(a, sm, threadIdx.x, blockIdx.x, blockIdx.y))
+    return;
+  __syncthreads();
+  for (int r = th.j0 - 1; r <= th.j1; ++r)
+  {
+    th.phaseA(a, sm, r);
+    __syncthreads();
+    th.phaseB(a, sm, r);
+  }
+  if (FUSE_DT && a.invdt_bits)
+    block_max_to_global(th.invdt, a.invdt_bits);
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar bookkeeping of the device-resident loop (src/main.cpp:100-143)
+// ------------------------------------------------------------------------------------------
+__global__ void
+k_loop_begin_step(LoopState * st, double cfl, double tEnd)
+{
+  if (st->done)
+    return;
+  const double invDt = __longlong_as_double((long long)st->invdt_cur);
+  double       dt = cfl / invDt; // HydroRun.h:246
+  if (st->t + dt > tEnd)         // main.cpp:131-134
+    dt = tEnd - st->t;
+  st->dt = dt;
+  st->invdt_next = 0ull;
+}
+
+__global__ void
+k_loop_end_step(LoopState * st, double tEnd, int max_steps, double * dt_hist, long hist_cap)
+{
+  if (st->done)
+    return;
+  if (dt_hist && st->nStep < hist_cap)
+    dt_hist[st->nStep] = st->dt;
+  st->nStep += 1; // main.cpp:142-143
+  st->t += st->dt;
+  st->invdt_cur = st->invdt_next;
+  st->done = !(st->t < tEnd && st->nStep < max_steps); // main.cpp:100
+}
+
+// ------------------------------------------------------------------------------------------
+// function-level evaluation (known-answer tests of the __device__ functions)
+// ------------------------------------------------------------------------------------------
+__global__ void
+k_eval(Settings s, int func, const double * __restrict__ in, double * __restrict__ out, long n)
+{
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n)
+    return;
+  switch (func)
+  {
+    case 0:
+    { // prim
+      const double * a = in + 4 * r;
+      double *       o = out + 5 * r;
+      compute_primitives(s, a[ID], a[IP], a[IU], a[IV], o[ID], o[IP], o[IU], o[IV], o[4]);
+      break;
+    }
+    case 1:
+    { // slope
+      const double * a = in + 20 * r;
+      double *       o = out + 8 * r;
+      double         dq[4];
+      slopes_dir(s, a, a + 4, a + 8, dq);
+      for (int v = 0; v < 4; ++v)
+        o[v] = dq[v];
+      slopes_dir(s, a, a + 12, a + 16, dq);
+      for (int v = 0; v < 4; ++v)
+        o[4 + v] = dq[v];
+      break;
+    }
+    case 2:
+    { // trace
+      const double * a = in + 14 * r;
+      double *       o = out + 16 * r;
+      double         s0[4], f[4];
+      trace_sources(s, a, a + 4, a + 8, s0);
+      trace_face<-1>(s, a, a + 4, s0, a[12], f);
+      for (int v = 0; v < 4; ++v)
+        o[v] = f[v];
+      trace_face<+1>(s, a, a + 4, s0, a[12], f);
+      for (int v = 0; v < 4; ++v)
+        o[4 + v] = f[v];
+      trace_face<-1>(s, a, a + 8, s0, a[13], f);
+      for (int v = 0; v < 4; ++v)
+        o[8 + v] = f[v];
+      trace_face<+1>(s, a, a + 8, s0, a[13], f);
+      for (int v = 0; v < 4; ++v)
+        o[12 + v] = f[v];
+      break;
+    }
+    case 3:
+    case 6:
+    { // hllc / hll
+      const double * a = in + 8 * r;
+      double *       o = out + 4 * r;
+      if (func == 3)
+        riemann_hllc(s, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP],
+                     o[IU], o[IV]);
+      else
+        riemann_hll(s, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP],
+                    o[IU], o[IV]);
+      break;
+    }
+    case 4:
+    { // approx
+      const double * a = in + 8 * r;
+      double *       o = out + 8 * r;
+      riemann_approx(s, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP],
+                     o[IU], o[IV], o[4 + ID], o[4 + IP], o[4 + IU], o[4 + IV]);
+      break;
+    }
+    case 5:
+    { // cmpflx
+      const double * a = in + 4 * r;
+      double *       o = out + 4 * r;
+      cmpflx(s, a[ID], a[IP], a[IU], a[IV], o[ID], o[IP], o[IU], o[IV]);
+      break;
+    }
+  }
+}
+
+} // namespace
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+Settings
+make_settings(const e2d_params & p)
+{
+  Settings s;
+  s.gamma0 = p.gamma0;
+  s.gamma6 = p.gamma6;
+  s.cfl = p.cfl;
+  s.slope_type = p.slope_type;
+  s.smallr = p.smallr;
+  s.smallc = p.smallc;
+  s.smallp = p.smallp;
+  s.smallpp = p.smallpp;
+  s.dx = p.dx;
+  s.dy = p.dy;
+  return s;
+}
+
+Geom
+make_geom(const e2d_params & p, int jsize_loc, int j_off)
+{
+  Geom g;
+  g.isize = p.isize;
+  g.jsize = jsize_loc;
+  g.nx = p.nx;
+  g.ny = jsize_loc - 2 * p.ghostWidth;
+  g.j_off = j_off;
+  return g;
+}
+
+int
+solver_for(const e2d_params & p)
+{
+  // the reference parses `riemann=` and never reads it: every kernel hard-codes riemann_hllc
+  // (src/HydroRunFunctors.h:567,631)
+  return p.honourRiemannSolver ? p.riemannSolverType : E2D_RIEMANN_HLLC;
+}
+
+static inline dim3
+grid_rows(int ncols, int nrows, int block)
+{
+  return dim3((unsigned)((ncols + block - 1) / block), (unsigned)nrows, 1);
+}
+
+cudaError_t
+launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream_t st)
+{
+  InitArgs a;
+  a.problem = p.problemType;
+  a.xmin = p.xmin;
+  a.ymin = p.ymin;
+  a.dx = p.dx;
+  a.dy = p.dy;
+  a.gamma0 = p.gamma0;
+  a.blast_radius = p.blast_radius;
+  a.blast_center_x = p.blast_center_x;
+  a.blast_center_y = p.blast_center_y;
+  a.blast_density_in = p.blast_density_in;
+  a.blast_density_out = p.blast_density_out;
+  a.blast_pressure_in = p.blast_pressure_in;
+  a.blast_pressure_out = p.blast_pressure_out;
+  a.blast_energy_density = -1.0;
+  a.bubble_radius = p.bubble_radius;
+  a.bubble_center_x = p.bubble_center_x;
+  a.bubble_center_y = p.bubble_center_y;
+  a.bubble_density = p.bubble_density;
+  a.bubble_pressure = p.bubble_pressure;
+  a.preshock_density = p.preshock_density;
+  a.preshock_pressure = p.preshock_pressure;
+  a.postshock_density = p.postshock_density;
+  a.postshock_pressure = p.postshock_pressure;
+  a.postshock_velocity = p.postshock_velocity;
+  a.shock_loc = p.shock_loc;
+
+  const dim3 grid = grid_rows(g.isize, g.jsize, 128);
+  if (p.problemType == E2D_PROBLEM_BLAST && p.blast_total_energy_inside > 0)
+  {
+    // Sedov variant (:1445-1463): count the cells inside the disc, form the volume the way a serial
+    // Kokkos::Sum would (repeated += dx*dy), then overwrite the energy inside with E_tot / volume.
+    unsigned long long * d_n = nullptr;
+    cudaError_t          e = cudaMalloc(&d_n, sizeof(unsigned long long));
+    if (e != cudaSuccess)
+      return e;
+    cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st);
+    k_init_problem<<<grid, 128, 0, st>>>(g, a, U, d_n);
+    count_launch();
+    unsigned long long n_inside = 0;
+    cudaMemcpyAsync(&n_inside, d_n, sizeof n_inside, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cudaFree(d_n);
+    if (e != cudaSuccess)
+      return e;
+    double volume = 0.0;
+    for (unsigned long long k = 0; k < n_inside; ++k)
+      volume += p.dx * p.dy;
+    a.blast_energy_density = p.blast_total_energy_inside / volume;
+  }
+  k_init_problem<<<grid, 128, 0, st>>>(g, a, U, nullptr);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_make_boundaries(const e2d_params & p, const Geom & g, double * U, int faces, const int * d_done,
+                       cudaStream_t st)
+{
+  BcArgs a;
+  a.bc_xmin = p.boundary_type_xmin;
+  a.bc_xmax = p.boundary_type_xmax;
+  a.bc_ymin = p.boundary_type_ymin;
+  a.bc_ymax = p.boundary_type_ymax;
+  a.faces = faces;
+  const int n = 4 * g.isize + 4 * g.jsize;
+  k_make_boundaries<<<(n + 127) / 128, 128, 0, st>>>(g, a, U, d_done);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_reduce_invdt(const e2d_params & p, const Geom & g, const double * U, unsigned long long * d_bits,
+                    cudaStream_t st)
+{
+  const int bx = (g.nx + 255) / 256;
+  int       by = g.ny < 1 ? 1 : g.ny;
+  // enough blocks to fill the machine, few enough that the atomics stay negligible
+  const int max_by = (148 * 8 + bx - 1) / bx;
+  if (by > max_by)
+    by = max_by;
+  k_reduce_invdt<<<dim3(bx < 1 ? 1 : bx, by), 256, 0, st>>>(g, make_settings(p), U, d_bits);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_convert_to_primitives(const e2d_params & p, const Geom & g, const double * U, double * Q, cudaStream_t st)
+{
+  k_convert_to_primitives<<<grid_rows(g.isize, g.jsize, 256), 256, 0, st>>>(g, make_settings(p), U, Q);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_compute_and_store_fluxes(const e2d_params & p, const Geom & g, const double * Q, double * Fx, double * Fy,
+                                double dtdx, double dtdy, cudaStream_t st)
+{
+  const dim3     grid = grid_rows(g.isize - 3, g.jsize - 3, 128);
+  const Settings s = make_settings(p);
+  switch (solver_for(p))
+  {
+    case E2D_RIEMANN_APPROX:
+      k_compute_and_store_fluxes<0><<<grid, 128, 0, st>>>(g, s, Q, Fx, Fy, dtdx, dtdy);
+      break;
+    case E2D_RIEMANN_HLL:
+      k_compute_and_store_fluxes<1><<<grid, 128, 0, st>>>(g, s, Q, Fx, Fy, dtdx, dtdy);
+      break;
+    default:
+      k_compute_and_store_fluxes<2><<<grid, 128, 0, st>>>(g, s, Q, Fx, Fy, dtdx, dtdy);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_update(const e2d_params &, const Geom & g, double * U, const double * Fx, const double * Fy, cudaStream_t st)
+{
+  k_update<<<grid_rows(g.nx, g.ny, 256), 256, 0, st>>>(g, U, Fx, Fy);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_compute_slopes(const e2d_params & p, const Geom & g, const double * Q, double * Sx, double * Sy,
+                      cudaStream_t st)
+{
+  k_compute_slopes<<<grid_rows(g.isize - 2, g.jsize - 2, 128), 128, 0, st>>>(g, make_settings(p), Q, Sx, Sy);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_trace_and_fluxes(const e2d_params & p, const Geom & g, const double * Q, const double * Sx, const double * Sy,
+                        double * F, double dtdx, double dtdy, int dir, cudaStream_t st)
+{
+  const dim3     grid = grid_rows(g.isize - 3, g.jsize - 3, 128);
+  const Settings s = make_settings(p);
+  const int      sol = solver_for(p);
+#define E2D_TF(SOL, DIR) k_trace_and_fluxes<SOL, DIR><<<grid, 128, 0, st>>>(g, s, Q, Sx, Sy, F, dtdx, dtdy)
+  if (dir == 1)
+  {
+    if (sol == 0)
+      E2D_TF(0, 1);
+    else if (sol == 1)
+      E2D_TF(1, 1);
+    else
+      E2D_TF(2, 1);
+  }
+  else
+  {
+    if (sol == 0)
+      E2D_TF(0, 2);
+    else if (sol == 1)
+      E2D_TF(1, 2);
+    else
+      E2D_TF(2, 2);
+  }
+#undef E2D_TF
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_update_dir(const e2d_params &, const Geom & g, double * U, const double * F, int dir, cudaStream_t st)
+{
+  if (dir == 1)
+    k_update_dir<1><<<grid_rows(g.nx, g.ny, 256), 256, 0, st>>>(g, U, F);
+  else
+    k_update_dir<2><<<grid_rows(g.nx, g.ny, 256), 256, 0, st>>>(g, U, F);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// rows per block segment: as long as possible (2 warm-up rows per segment are redundant work) while
+// still cutting the grid into enough blocks to keep 148 SMs x 3 resident blocks busy for several waves
+static int
+choose_seg_rows(int nbx, int ny)
+{
+  const int slots = 148 * kMarchMinBlocks;
+  int       best = ny;
+  for (int waves = 8; waves >= 1; --waves)
+  {
+    const int want_blocks = slots * waves;
+    int       nseg = (want_blocks + nbx - 1) / nbx;
+    if (nseg < 1)
+      nseg = 1;
+    int rows = (ny + nseg - 1) / nseg;
+    if (rows >= 32)
+    {
+      best = rows;
+      break;
+    }
+    best = rows < 8 ? 8 : rows;
+  }
+  if (best > ny)
+    best = ny;
+  if (best < 1)
+    best = 1;
+  return best;
+}
+
+cudaError_t
+launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
+                  const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done, cudaStream_t st)
+{
+  MarchArgs a;
+  a.Uin = Uin;
+  a.Uout = Uout;
+  a.isize = g.isize;
+  a.jsize = g.jsize;
+  a.s = make_settings(p);
+  a.dt = dt;
+  a.d_dt = d_dt;
+  a.invdt_bits = d_invdt_bits;
+  const int nbx = (g.nx + (kBX - 4) - 1) / (kBX - 4);
+  a.seg_rows = choose_seg_rows(nbx, g.ny);
+  const int  nseg = (g.ny + a.seg_rows - 1) / a.seg_rows;
+  const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
+  const int  sol = solver_for(p);
+  const bool fuse = d_invdt_bits != nullptr;
+#define E2D_FS(SOL)                                              \
+  do                                                             \
+  {                                                              \
+    if (fuse)                                                    \
+      k_fused_step<SOL, true><<<grid, kBX, 0, st>>>(a, d_done);  \
+    else                                                         \
+      k_fused_step<SOL, false><<<grid, kBX, 0, st>>>(a, d_done); \
+  } while (0)
+  if (sol == 0)
+    E2D_FS(0);
+  else if (sol == 1)
+    E2D_FS(1);
+  else
+    E2D_FS(2);
+#undef E2D_FS
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_loop_begin_step(LoopState * st_dev, double cfl, double tEnd, cudaStream_t st)
+{
+  k_loop_begin_step<<<1, 1, 0, st>>>(st_dev, cfl, tEnd);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_loop_end_step(LoopState * st_dev, double tEnd, int max_steps, double * dt_hist, long hist_cap,
+                     cudaStream_t st)
+{
+  k_loop_end_step<<<1, 1, 0, st>>>(st_dev, tEnd, max_steps, dt_hist, hist_cap);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_eval(const e2d_params & p, int func, const double * d_in, double * d_out, long n, cudaStream_t st)
+{
+  k_eval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(make_settings(p), func, d_in, d_out, n);
+  count_launch();
+  return cudaGetLastError();
+}
+
+} // namespace e2d

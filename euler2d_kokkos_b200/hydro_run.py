@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's driver surface, over the C ABI.
+
+``HydroParams`` <-> struct HydroParams (src/HydroParams.h:155-265, setup/init in HydroParams.cpp:43-190)
+``HydroRun``    <-> class euler2d::HydroRun<device_t> (src/HydroRun.h:44-134): same method names and
+                    argument meaning (compute_dt(useU), make_boundaries(Udata), godunov_unsplit(nStep, dt),
+                    saveData(Udata, iStep, name)), plus ``run()`` = the loop of src/main.cpp:100-143 kept on
+                    the device.
+All compute happens in libeuler2d_b200.so on the GPU; numpy is only used to hand arrays to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import E2D_U, E2D_U2, E2D_Q, LAYOUT_SOA, LAYOUT_KOKKOS_OMP, Params, RunStats, Slab, check, lib
+
+
+class HydroParams:
+    """Parameters read from an .ini with the reference's semantics (floats go through strtof)."""
+
+    def __init__(self, raw: Params | None = None):
+        object.__setattr__(self, "raw", raw if raw is not None else Params())
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_ini(cls, path: str, strict: bool = True) -> "HydroParams":
+        p = Params()
+        rc = lib().e2d_params_from_ini(path.encode(), C.byref(p))
+        if rc != 0 and strict:
+            check(rc, f"e2d_params_from_ini({path})")
+        return cls(p)
+
+    @classmethod
+    def from_string(cls, text: str) -> "HydroParams":
+        p = Params()
+        check(lib().e2d_params_from_string(text.encode(), C.byref(p)), "e2d_params_from_string")
+        return cls(p)
+
+    def setup(self, ini_path: str) -> None:  # HydroParams::setup(ConfigMap&)
+        p = Params()
+        check(lib().e2d_params_from_ini(ini_path.encode(), C.byref(p)), "e2d_params_from_ini")
+        object.__setattr__(self, "raw", p)
+
+    def init(self) -> None:  # HydroParams::init()
+        check(lib().e2d_params_init(C.byref(self.raw)), "e2d_params_init")
+
+    def print(self) -> None:  # HydroParams::print()
+        lib().e2d_params_print(C.byref(self.raw))
+
+    def copy(self) -> "HydroParams":
+        return HydroParams(self.raw.copy())
+
+    # -- attribute passthrough ------------------------------------------------------------------
+    def __getattr__(self, name):
+        raw = object.__getattribute__(self, "raw")
+        if name in dict(Params._fields_):
+            v = getattr(raw, name)
+            return v.decode() if isinstance(v, bytes) else v
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in dict(Params._fields_):
+            setattr(self.raw, name, value.encode() if isinstance(value, str) else value)
+        else:
+            raise AttributeError(f"HydroParams has no field {name}")
+
+
+class HydroRun:
+    """Drop-in for euler2d::HydroRun<device_t> on one GPU (or one y-slab of a multi-GPU run)."""
+
+    U = E2D_U
+    U2 = E2D_U2
+    Q = E2D_Q
+
+    def __init__(self, params: HydroParams, slab: Slab | None = None, stream: int | None = None,
+                 U_ptr: int | None = None, U2_ptr: int | None = None):
+        self.params = params
+        self._h = C.c_void_p()
+        check(lib().e2d_create(C.byref(params.raw), C.byref(slab) if slab is not None else None,
+                               U_ptr, U2_ptr, stream, C.byref(self._h)), "e2d_create")
+        self.jsize_loc = (slab.ny_loc if slab is not None else params.ny) + 2 * params.ghostWidth
+        self.isize = params.isize
+        self.shape = (4, self.jsize_loc, self.isize)
+
+    def close(self) -> None:
+        if self._h:
+            lib().e2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the reference's methods ----------------------------------------------------------------
+    def compute_dt(self, useU: int) -> float:
+        dt = C.c_double()
+        check(lib().e2d_compute_dt(self._h, int(useU), C.byref(dt), None), "e2d_compute_dt")
+        return dt.value
+
+    def compute_invdt_local(self, useU: int) -> float:
+        dt, inv = C.c_double(), C.c_double()
+        check(lib().e2d_compute_dt(self._h, int(useU), C.byref(dt), C.byref(inv)), "e2d_compute_dt")
+        return inv.value
+
+    def make_boundaries(self, Udata: int) -> None:
+        check(lib().e2d_make_boundaries(self._h, int(Udata)), "e2d_make_boundaries")
+
+    def godunov_unsplit(self, nStep: int, dt: float, fill_boundaries: bool = True) -> None:
+        fn = lib().e2d_godunov_unsplit if fill_boundaries else lib().e2d_godunov_unsplit_nobc
+        check(fn(self._h, int(nStep), float(dt)), "e2d_godunov_unsplit")
+
+    def saveData(self, Udata: int, iStep: int, name: str = "U") -> None:
+        if self.params.ioVTK:
+            check(lib().e2d_save_vtk(self._h, int(Udata), int(iStep)), "e2d_save_vtk")
+
+    # -- device-resident loop -------------------------------------------------------------------
+    def run(self, max_steps: int = -1) -> RunStats:
+        st = RunStats()
+        check(lib().e2d_run(self._h, int(max_steps), C.byref(st)), "e2d_run")
+        return st
+
+    def dt_history(self) -> np.ndarray:
+        cap = max(int(self.params.nStepmax), 1) + 1 << 1
+        buf = np.zeros(max(cap, 1 << 16))
+        n = C.c_long()
+        check(lib().e2d_get_dt_history(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), buf.size, C.byref(n)),
+              "e2d_get_dt_history")
+        return buf[: n.value].copy()
+
+    def set_time(self, t: float, nStep: int) -> None:
+        check(lib().e2d_set_time(self._h, float(t), int(nStep)), "e2d_set_time")
+
+    # -- data movement --------------------------------------------------------------------------
+    def download(self, which: int = E2D_U, layout: int = LAYOUT_SOA) -> np.ndarray:
+        if layout == LAYOUT_SOA:
+            out = np.empty(self.shape)
+        else:
+            out = np.empty((self.isize, self.jsize_loc, 4))
+        check(lib().e2d_download(self._h, int(which), out.ctypes.data, layout), "e2d_download")
+        return out
+
+    def upload(self, which: int, host: np.ndarray, layout: int = LAYOUT_SOA) -> None:
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        assert host.size == 4 * self.jsize_loc * self.isize
+        check(lib().e2d_upload(self._h, int(which), host.ctypes.data, layout), "e2d_upload")
+
+    def step_host(self, U_in: np.ndarray, U_out: np.ndarray) -> float:
+        """One step for a caller whose state lives in host memory (H2D, boundaries, dt, step, D2H)."""
+        dt = C.c_double()
+        check(lib().e2d_step_host(self._h, U_in.ctypes.data, U_out.ctypes.data, C.byref(dt)), "e2d_step_host")
+        return dt.value
+
+    def step_host_ptr(self, in_ptr: int, out_ptr: int) -> float:
+        dt = C.c_double()
+        check(lib().e2d_step_host(self._h, in_ptr, out_ptr, C.byref(dt)), "e2d_step_host")
+        return dt.value
+
+    def device_ptr(self, which: int) -> int:
+        return lib().e2d_device_ptr(self._h, int(which)) or 0
+
+    @property
+    def stream(self) -> int:
+        return lib().e2d_stream(self._h) or 0
+
+    def synchronize(self) -> None:
+        check(lib().e2d_synchronize(self._h), "e2d_synchronize")
+
+    def enable_timers(self, on: bool = True) -> None:
+        check(lib().e2d_enable_timers(self._h, int(on)), "e2d_enable_timers")
+
+    def timers(self) -> dict:
+        out = (C.c_double * 5)()
+        check(lib().e2d_get_timers(self._h, out), "e2d_get_timers")
+        return dict(zip(("boundaries", "godunov", "primitive", "fluxes", "update"), list(out)))
+
+
+def main_loop(ini_path: str, verbose: bool = True, device_loop: bool = False):
+    """The program of src/main.cpp:76-204 through the HydroRun mirror. Returns (hydro, nStep, t)."""
+    import time
+
+    params = HydroParams.from_ini(ini_path)
+    if verbose:
+        print(f"Using Euler implementation version {params.implementationVersion}")
+        params.print()
+    hydro = HydroRun(params)
+    t, nStep = 0.0, 0
+    dt = hydro.compute_dt(nStep % 2)          # main.cpp:87
+    hydro.make_boundaries(HydroRun.U)         # main.cpp:90-91
+    hydro.make_boundaries(HydroRun.U2)
+    if verbose:
+        print("Start computation....")
+    t0 = time.perf_counter()
+    if device_loop and not (params.enableOutput and params.nOutput > 0):
+        st = hydro.run()
+        nStep, t = st.nStep, st.t
+    else:
+        while t < params.tEnd and nStep < params.nStepmax:  # main.cpp:100
+            if verbose and nStep % 10 == 0:
+                print("time step=%7d (dt=% 10.8f t=% 10.8f)" % (nStep, dt, t))
+            if params.enableOutput and params.nOutput > 0 and nStep % params.nOutput == 0:
+                if verbose:
+                    print(f"Output results at time t={t:g} step {nStep} dt={dt:g}")
+                hydro.saveData(HydroRun.U if nStep % 2 == 0 else HydroRun.U2, nStep, "U")
+            dt = hydro.compute_dt(nStep % 2)  # main.cpp:128
+            if t + dt > params.tEnd:          # main.cpp:131-134
+                dt = params.tEnd - t
+            hydro.godunov_unsplit(nStep, dt)  # main.cpp:139
+            nStep += 1
+            t += dt
+        if params.enableOutput and params.nOutput > 0:
+            hydro.saveData(HydroRun.U if nStep % 2 == 0 else HydroRun.U2, nStep, "U")
+    hydro.synchronize()
+    t_tot = time.perf_counter() - t0
+    if verbose:
+        print("total           time : %5.3f secondes" % t_tot)
+        print("Perf                 : %10.2f number of Mcell-updates/s"
+              % (1.0 * nStep * params.isize * params.jsize / t_tot * 1e-6))
+    return hydro, nStep, t

@@ -1,0 +1,245 @@
+/* euler2d_b200 — C ABI of the B200-native unsplit MUSCL-Hancock Godunov step.
+ *
+ * This is the drop-in boundary for the hot path of pkestene/euler2d_kokkos.  The reference has no
+ * FFI; its seam is the C++ class euler2d::HydroRun<device_t> (src/HydroRun.h:44-134) as driven by
+ * src/main.cpp:76-143, plus the static XxxFunctor::apply() operators underneath it
+ * (src/HydroRunFunctors.h).  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all arrays are fp64, SoA planes  off = i + isize*(j + jsize*var)
+ *     (= Kokkos LayoutLeft of DataArray, src/kokkos_shared.h:21), var: 0 rho, 1 E (or p), 2 rho*u (u), 3 rho*v (v)
+ *   - every function returns an e2d_status (0 = ok); nothing throws, nothing calls exit()
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream)
+ *   - kernel-level entry points (e2d_k_*) take DEVICE pointers and only enqueue work
+ *   - there is no CPU fallback: without a CUDA device every compute call returns E2D_ERR_CUDA
+ *   - a "slab" is a horizontal strip of the global grid owned by one GPU: isize x jsize_loc cells
+ *     including 2 ghost rows on each side; local row j is global row j + j_off.  The whole domain is
+ *     the slab jsize_loc = jsize, j_off = 0.
+ */
+#ifndef EULER2D_B200_H
+#define EULER2D_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum e2d_status
+{
+  E2D_OK = 0,
+  E2D_ERR_INVALID = 1, /* bad argument */
+  E2D_ERR_IO = 2,      /* cannot open / write a file */
+  E2D_ERR_CUDA = 3,    /* CUDA runtime error or no device (see e2d_last_error) */
+  E2D_ERR_ALLOC = 4,
+  E2D_ERR_UNSUPPORTED = 5
+} e2d_status;
+
+/* component / face / boundary / problem ids: src/HydroParams.h:27-104 */
+enum { E2D_ID = 0, E2D_IP = 1, E2D_IE = 1, E2D_IU = 2, E2D_IV = 3, E2D_NBVAR = 4 };
+enum { E2D_FACE_XMIN = 0, E2D_FACE_XMAX = 1, E2D_FACE_YMIN = 2, E2D_FACE_YMAX = 3 };
+enum { E2D_BC_UNDEFINED = 0, E2D_BC_DIRICHLET = 1, E2D_BC_NEUMANN = 2, E2D_BC_PERIODIC = 3, E2D_BC_COPY = 4 };
+enum { E2D_PROBLEM_IMPLODE = 0, E2D_PROBLEM_BLAST = 1, E2D_PROBLEM_FOUR_QUADRANT = 2,
+       E2D_PROBLEM_DISCONTINUITY = 3, E2D_PROBLEM_SHOCKED_BUBBLE = 4 };
+enum { E2D_RIEMANN_APPROX = 0, E2D_RIEMANN_HLL = 1, E2D_RIEMANN_HLLC = 2 };
+/* bit mask of faces for e2d_k_make_boundaries */
+enum { E2D_FACES_X = 3, E2D_FACES_YMIN = 4, E2D_FACES_YMAX = 8, E2D_FACES_ALL = 15 };
+/* host array layouts for upload / download */
+enum { E2D_LAYOUT_SOA = 0,      /* [var][j][i]   (device layout, Kokkos LayoutLeft)          */
+       E2D_LAYOUT_KOKKOS_OMP = 1 /* (i*jsize+j)*4+var (Kokkos LayoutRight = the OpenMP build) */ };
+
+/* Replaces: struct HydroParams + HydroSettings + ShockedBubbleParams (src/HydroParams.h:107-265). */
+typedef struct e2d_params
+{
+  int    nStepmax;
+  double tEnd;
+  int    nOutput;
+  int    enableOutput;
+  int    nx, ny, ghostWidth, imin, imax, jmin, jmax, isize, jsize;
+  double xmin, xmax, ymin, ymax, dx, dy;
+  int    boundary_type_xmin, boundary_type_xmax, boundary_type_ymin, boundary_type_ymax;
+  int    ioVTK, ioHDF5;
+  double gamma0, gamma6, cfl, slope_type, smallr, smallc, smallp, smallpp; /* HydroSettings */
+  int    niter_riemann, riemannSolverType, problemType;
+  double blast_radius, blast_center_x, blast_center_y, blast_density_in, blast_density_out;
+  double blast_pressure_in, blast_pressure_out, blast_total_energy_inside;
+  int    blast_nbins;
+  double bubble_radius, bubble_center_x, bubble_center_y, bubble_density, bubble_pressure;
+  double preshock_density, preshock_pressure, postshock_density, postshock_pressure, postshock_velocity;
+  double shock_loc;
+  int    implementationVersion;
+  /* [output] outputDir / outputPrefix, read by HydroRun::saveVTK (src/HydroRun.h:526-527) */
+  char   outputDir[256];
+  char   outputPrefix[256];
+  /* extension (not in the reference, where `riemann=` is parsed but never used — SURVEY.md §0.4):
+   * 0 = reference behaviour (every kernel solves HLLC), 1 = honour riemannSolverType. */
+  int    honourRiemannSolver;
+} e2d_params;
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+const char * e2d_version(void);
+const char * e2d_status_string(int status);
+/* message of the last failing CUDA/IO call on this thread ("" if none) */
+const char * e2d_last_error(void);
+/* number of CUDA devices visible (0 without a driver/GPU); never fails */
+int          e2d_device_count(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long e2d_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* parameters: ConfigMap + HydroParams::setup + HydroParams::init                             */
+/*   replaces config/ConfigMap.{h,cpp}, config/inih/*, src/HydroParams.cpp:43-190             */
+/*   (all reals go through strtof, exactly like ConfigMap::getFloat)                          */
+/* ------------------------------------------------------------------------------------------ */
+int e2d_params_from_ini(const char * path, e2d_params * out);
+/* same, from an in-memory .ini text (used by tests and by callers that build decks on the fly) */
+int e2d_params_from_string(const char * ini_text, e2d_params * out);
+/* recompute the derived fields after editing nx/ny/xmin/... (HydroParams::init, :161-190) */
+int e2d_params_init(e2d_params * p);
+/* HydroParams::print (src/HydroParams.cpp:196-224), same text, to stdout */
+int e2d_params_print(const e2d_params * p);
+
+/* ------------------------------------------------------------------------------------------ */
+/* kernel-level operators (device pointers; replace the XxxFunctor::apply statics)            */
+/* ------------------------------------------------------------------------------------------ */
+/* Init{Implode,Blast,FourQuadrant,Discontinuity,ShockedBubble}Functor::apply
+ * (src/HydroRunFunctors.h:1347-1827) on a slab; fills ghosts too, like the reference. */
+int e2d_k_init_problem(const e2d_params * p, double * U, int jsize_loc, int j_off, void * stream);
+
+/* MakeBoundariesFunctor<face>::apply x4 in the order of HydroRun::make_boundaries
+ * (src/HydroRunFunctors.h:1832-2030, src/HydroRun.h:390-399), as ONE launch.  faces = bit mask. */
+int e2d_k_make_boundaries(const e2d_params * p, double * U, int jsize_loc, int faces, void * stream);
+
+/* ComputeDtFunctor::apply (src/HydroRunFunctors.h:17-79): d_invdt[0] = max(d_invdt[0], max over the
+ * slab's interior cells of (c+|u|)/dx + (c+|v|)/dy).  d_invdt is a DEVICE double the caller has set
+ * to 0 (non-negative values only: the reduction is an integer atomicMax on the bit pattern). */
+int e2d_k_reduce_invdt(const e2d_params * p, const double * U, int jsize_loc, double * d_invdt, void * stream);
+
+/* ConvertToPrimitivesFunctor::apply (src/HydroRunFunctors.h:84-143) */
+int e2d_k_convert_to_primitives(const e2d_params * p, const double * U, double * Q, int jsize_loc, void * stream);
+
+/* ComputeAndStoreFluxesFunctor::apply (src/HydroRunFunctors.h:412-651): Fx, Fy = flux*dt/dx, flux*dt/dy */
+int e2d_k_compute_and_store_fluxes(const e2d_params * p, const double * Q, double * Fx, double * Fy,
+                                   double dtdx, double dtdy, int jsize_loc, void * stream);
+
+/* UpdateFunctor::apply (src/HydroRunFunctors.h:656-723) */
+int e2d_k_update(const e2d_params * p, double * U, const double * Fx, const double * Fy, int jsize_loc,
+                 void * stream);
+
+/* implementation-1 trio (src/HydroRunFunctors.h:986-1342): dir = 1 (XDIR) or 2 (YDIR) */
+int e2d_k_compute_slopes(const e2d_params * p, const double * Q, double * Sx, double * Sy, int jsize_loc,
+                         void * stream);
+int e2d_k_compute_trace_and_fluxes(const e2d_params * p, const double * Q, const double * Sx, const double * Sy,
+                                   double * F, double dtdx, double dtdy, int dir, int jsize_loc, void * stream);
+int e2d_k_update_dir(const e2d_params * p, double * U, const double * F, int dir, int jsize_loc, void * stream);
+
+/* The fused single-kernel step — replaces ConvertToPrimitives + ComputeFluxesAndUpdateFunctor::apply
+ * (src/HydroRunFunctors.h:728-980, "implementationVersion 2") *and* the deep_copy of
+ * src/HydroRun.h:302, deterministically (no atomics on the state): reads Uin (ghosts filled),
+ * writes the interior of Uout, bit-identical to the unfused implementation 0.
+ *   dt         time step (used when d_dt == NULL)
+ *   d_dt       optional DEVICE pointer to dt (device-resident time loop)
+ *   d_invdt    optional DEVICE double (set to 0 by the caller): receives the CFL reduction
+ *              (ComputeDtFunctor) of the NEW state, fused in the epilogue
+ */
+int e2d_k_fused_step(const e2d_params * p, const double * Uin, double * Uout, int jsize_loc, double dt,
+                     const double * d_dt, double * d_invdt, void * stream);
+
+/* per-cell device functions of HydroBaseFunctor (src/HydroBaseFunctor.h) evaluated on the GPU over
+ * n records of HOST doubles — function-level known-answer tests.
+ *   func     in (doubles per record)                          out
+ *   "prim"   u[4]                                             q[4], c              computePrimitives :76-102
+ *   "slope"  q, qPlusX, qMinusX, qPlusY, qMinusY (20)         dqX[4], dqY[4]       slope_unsplit_hydro_2d :473-516
+ *   "trace"  q, dqX, dqY, dtdx, dtdy (14)                     XMIN,XMAX,YMIN,YMAX  trace_unsplit_2d_along_dir :214-291
+ *   "hllc"   qleft, qright (8)                                flux[4]              riemann_hllc :704-809
+ *   "approx" qleft, qright (8)                                qgdnv[4], flux[4]    riemann_approx :558-693
+ *   "cmpflx" qgdnv (4)                                        flux[4]              cmpflx :523-547
+ *   "hll"    qleft, qright (8)                                flux[4]              (extension: not in the reference)
+ */
+int e2d_k_eval_host(const e2d_params * p, const char * func, const double * in, double * out, long n);
+
+/* ------------------------------------------------------------------------------------------ */
+/* HydroRun handle (replaces class euler2d::HydroRun<device_t>, src/HydroRun.h:44-399)        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct e2d_handle e2d_handle;
+
+/* which array */
+enum { E2D_U = 0, E2D_U2 = 1, E2D_Q = 2 };
+
+/* y-slab description for multi-GPU runs; NULL in e2d_create = whole domain on the current device */
+typedef struct e2d_slab
+{
+  int rank, nranks;
+  int ny_loc; /* interior rows owned by this rank */
+  int j_off;  /* global row index (ghosts included) of local row 0 */
+} e2d_slab;
+
+/* HydroRun::HydroRun (src/HydroRun.h:143-216): allocate U, U2 (+ scratch), run the problem
+ * initialiser, U2 = U.  Uses the CURRENT CUDA device and creates its own stream unless `stream`
+ * is given.  U_ext/U2_ext: optional caller-owned device buffers (isize*jsize_loc*4 doubles). */
+int e2d_create(const e2d_params * p, const e2d_slab * slab, double * U_ext, double * U2_ext, void * stream,
+               e2d_handle ** out);
+int e2d_destroy(e2d_handle * h);
+
+/* HydroRun::compute_dt(useU) (src/HydroRun.h:229-251): *dt = cfl / max(invDt). Synchronous.
+ * On a slab, *invdt_local (may be NULL) returns this rank's partial max so the caller can
+ * allreduce(max) it and form dt = cfl/invDt itself. */
+int e2d_compute_dt(e2d_handle * h, int useU, double * dt, double * invdt_local);
+/* HydroRun::make_boundaries(Udata) (src/HydroRun.h:390-399); which = E2D_U | E2D_U2.
+ * On a slab only the faces this rank owns are filled (x always; ymin on rank 0; ymax on the last). */
+int e2d_make_boundaries(e2d_handle * h, int which);
+/* HydroRun::godunov_unsplit(nStep, dt) (src/HydroRun.h:259-364), honouring implementationVersion:
+ * 0 = store fluxes then update, 1 = slopes array + per-direction trace/flux/update, 2 = fused kernel. */
+int e2d_godunov_unsplit(e2d_handle * h, int nStep, double dt);
+/* as above but skipping the make_boundaries(data_in) of src/HydroRun.h:296 — for slab runs where the
+ * caller has exchanged halos and filled boundaries itself */
+int e2d_godunov_unsplit_nobc(e2d_handle * h, int nStep, double dt);
+
+typedef struct e2d_run_stats
+{
+  int    nStep;        /* steps taken so far (total, across calls) */
+  double t;            /* simulation time reached */
+  double dt_last;      /* dt of the last step */
+  double seconds;      /* device time of this call's steps (CUDA events on the handle's stream) */
+  long long launches;  /* kernels launched by this call */
+} e2d_run_stats;
+
+/* The main loop of src/main.cpp:100-143 with IO off, device-resident: dt, t and nStep live in
+ * device memory, one fused kernel per step (boundary fill, step, next-step CFL reduction), no
+ * host synchronisation inside.  Continues from the handle's current (t, nStep); stops when
+ * t >= tEnd or nStep >= max_steps (max_steps < 0: params.nStepmax).  Whole-domain handles only. */
+int e2d_run(e2d_handle * h, long max_steps, e2d_run_stats * stats);
+/* dt used by each step taken through e2d_run so far (n_cap entries max); returns count in *n */
+int e2d_get_dt_history(e2d_handle * h, double * dts, long n_cap, long * n);
+/* reset (t, nStep) bookkeeping of e2d_run, e.g. after e2d_upload */
+int e2d_set_time(e2d_handle * h, double t, int nStep);
+
+/* Kokkos::deep_copy(Uhost, Udata) + raw access (src/HydroRun.h:522) */
+int e2d_download(e2d_handle * h, int which, double * host, int layout);
+int e2d_upload(e2d_handle * h, int which, const double * host, int layout);
+double * e2d_device_ptr(e2d_handle * h, int which);
+void *   e2d_stream(e2d_handle * h);
+int      e2d_synchronize(e2d_handle * h);
+int      e2d_get_params(e2d_handle * h, e2d_params * out);
+
+/* End-to-end entry for callers whose state lives in HOST memory (bench.py's e2e leg):
+ * H2D of U_host_in (SoA, whole slab incl. ghosts) -> make_boundaries -> compute_dt -> one
+ * godunov step -> D2H into U_host_out.  *dt_out receives the dt used.  Pinned host buffers make the
+ * copies asynchronous; pageable ones work too. */
+int e2d_step_host(e2d_handle * h, const double * U_host_in, double * U_host_out, double * dt_out);
+
+/* HydroRun::saveData -> saveVTK (src/HydroRun.h:486-609): ascii .vti, ghosts stripped,
+ * <outputDir>/<outputPrefix>_<%07d iStep>.vti, default ostream precision (6 significant digits). */
+int e2d_save_vtk(e2d_handle * h, int which, int iStep);
+
+/* the five public timers of HydroRun (src/HydroRun.h:74-75), seconds accumulated by the
+ * e2d_godunov_unsplit path when timing is enabled: [boundaries, godunov, primitive, fluxes, update] */
+int e2d_enable_timers(e2d_handle * h, int on);
+int e2d_get_timers(e2d_handle * h, double out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EULER2D_B200_H */

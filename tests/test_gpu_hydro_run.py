@@ -1,0 +1,229 @@
+"""GPU parity tests at the HydroRun level: the reference's driver loop (src/main.cpp:86-143) through the C ABI
+against the oracle — identical step count, identical dt sequence, identical bits in every interior cell."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import euler2d_kokkos_b200 as e2d
+import oracle
+from euler2d_kokkos_b200 import HydroRun
+from util import INNER, assert_bitwise, both_params, rel_errors
+
+pytestmark = pytest.mark.gpu
+
+SMALL = {"implode": (96, 48), "blast": (64, 96), "four_quadrant": (80, 80), "discontinuity": (72, 72),
+         "shocked_bubble": (178, 36)}
+
+
+def host_loop(hydro, params, max_steps):
+    """main.cpp:86-143 driven from the host, one compute_dt + godunov_unsplit per step."""
+    t, n, dts = 0.0, 0, []
+    dts.append(hydro.compute_dt(0))
+    hydro.make_boundaries(HydroRun.U)
+    hydro.make_boundaries(HydroRun.U2)
+    while t < params.tEnd and n < max_steps:
+        dt = hydro.compute_dt(n % 2)
+        if t + dt > params.tEnd:
+            dt = params.tEnd - t
+        hydro.godunov_unsplit(n, dt)
+        n += 1
+        t += dt
+        dts.append(dt)
+    return n, t, np.array(dts)
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("deck", list(SMALL))
+def test_host_driven_loop_bit_exact(deck, impl):
+    nx, ny = SMALL[deck]
+    hp, op = both_params(deck, mesh__nx=nx, mesh__ny=ny, other__implementationVersion=impl)
+    steps = 40
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, steps)
+    with HydroRun(hp) as hydro:
+        n, t, dts = host_loop(hydro, hp, steps)
+        U = hydro.download(HydroRun.U if n % 2 == 0 else HydroRun.U2)
+    assert n == n_ref and t == t_ref
+    assert_bitwise(dts, dts_ref, "dt sequence")
+    assert_bitwise(U[INNER], U_ref[INNER], f"{deck} impl {impl}")
+    if impl != 2:  # implementations 0/1 also reproduce the ghost cells (out = deep_copy(in), HydroRun.h:302)
+        assert_bitwise(U, U_ref, f"{deck} impl {impl} incl. ghosts")
+
+
+@pytest.mark.parametrize("deck", ["implode", "blast", "four_quadrant", "discontinuity", "shocked_bubble"])
+def test_device_resident_run_on_stock_decks(deck):
+    """The decks as shipped by the reference, 100 steps (SURVEY.md Appendix B pins these runs)."""
+    hp, op = both_params(deck, run__nOutput=-1)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 100)
+    with HydroRun(hp) as hydro:
+        hydro.make_boundaries(HydroRun.U)
+        hydro.make_boundaries(HydroRun.U2)
+        st = hydro.run(100)
+        U = hydro.download(HydroRun.U if st.nStep % 2 == 0 else HydroRun.U2)
+        dts = hydro.dt_history()
+    assert st.nStep == n_ref == 100
+    assert st.t == t_ref
+    assert_bitwise(dts, dts_ref[1:], "dt history")
+    assert_bitwise(U[INNER], U_ref[INNER], deck)
+    for l1, linf in rel_errors(U[INNER], U_ref[INNER]):  # north_star's stated tolerance, trivially met
+        assert l1 <= 1e-12 and linf <= 1e-12
+
+
+def test_run_until_tend_identical_step_count():
+    """four_quadrant stops on tEnd after 1029 steps at 256x256; here a smaller grid,
+    same mechanism: the clamp dt = tEnd - t (main.cpp:131-134) happens on the device."""
+    hp, op = both_params("four_quadrant", mesh__nx=64, mesh__ny=64, run__nOutput=-1)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op)
+    assert t_ref == op.tEnd and n_ref < op.nStepmax
+    with HydroRun(hp) as hydro:
+        st = hydro.run()
+        U = hydro.download(HydroRun.U if st.nStep % 2 == 0 else HydroRun.U2)
+        dts = hydro.dt_history()
+    assert st.nStep == n_ref and st.t == t_ref == hp.tEnd
+    assert_bitwise(dts, dts_ref[1:], "dt history")
+    assert_bitwise(U[INNER], U_ref[INNER], "four_quadrant to tEnd")
+
+
+def test_run_resumes_and_mixes_with_host_api():
+    hp, op = both_params("implode", mesh__nx=64, mesh__ny=40, run__nOutput=-1)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 31)
+    with HydroRun(hp) as hydro:
+        st = hydro.run(10)
+        assert st.nStep == 10
+        st = hydro.run(31)  # continue to a total of 31 (odd) steps
+        assert st.nStep == 31 and st.t == t_ref
+        U = hydro.download(HydroRun.U2)
+    assert_bitwise(U[INNER], U_ref[INNER], "resumed run")
+
+
+@pytest.mark.parametrize("bcs", [(3, 3, 3, 3), (3, 3, 2, 1), (2, 1, 3, 3)])
+@pytest.mark.parametrize("slope_type", [0, 1, 2])
+def test_boundary_and_slope_variants(bcs, slope_type):
+    hp, op = both_params("four_quadrant", mesh__nx=50, mesh__ny=70, hydro__slope_type=slope_type,
+                         mesh__boundary_type_xmin=bcs[0], mesh__boundary_type_xmax=bcs[1],
+                         mesh__boundary_type_ymin=bcs[2], mesh__boundary_type_ymax=bcs[3], run__nOutput=-1)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 60)
+    with HydroRun(hp) as hydro:
+        st = hydro.run(60)
+        U = hydro.download(HydroRun.U if st.nStep % 2 == 0 else HydroRun.U2)
+    assert st.nStep == n_ref and st.t == t_ref
+    assert_bitwise(U[INNER], U_ref[INNER], f"bc {bcs} slope {slope_type}")
+
+
+def test_step_host_round_trip():
+    hp, op = both_params("blast", mesh__nx=90, mesh__ny=60)
+    U0 = oracle.init_slab(op)
+    ref_in = U0.copy()
+    oracle.make_boundaries(op, ref_in)
+    dt_ref = op.cfl / oracle.compute_invdt(op, ref_in)
+    ref = oracle.godunov(op, ref_in, dt_ref)
+    out = np.empty_like(U0)
+    with HydroRun(hp) as hydro:
+        dt = hydro.step_host(U0, out)
+    assert dt == dt_ref
+    assert_bitwise(out[INNER], ref[INNER], "step_host")
+
+
+def test_upload_download_layouts():
+    hp, op = both_params("implode", mesh__nx=20, mesh__ny=12)
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(4, op.jsize, op.isize))
+    with HydroRun(hp) as hydro:
+        hydro.upload(HydroRun.U, A)
+        assert_bitwise(hydro.download(HydroRun.U), A)
+        K = hydro.download(HydroRun.U, e2d.LAYOUT_KOKKOS_OMP)  # (i, j, var) like the reference's OpenMP views
+        assert_bitwise(K, np.ascontiguousarray(A.transpose(2, 1, 0)))
+        hydro.upload(HydroRun.U2, K, e2d.LAYOUT_KOKKOS_OMP)
+        assert_bitwise(hydro.download(HydroRun.U2), A)
+
+
+def test_save_vtk_matches_reference_format(tmp_path):
+    hp, op = both_params("implode", mesh__nx=16, mesh__ny=8, output__outputDir=str(tmp_path),
+                         output__outputPrefix="vt")
+    with HydroRun(hp) as hydro:
+        hydro.saveData(HydroRun.U, 30, "U")
+        U = hydro.download(HydroRun.U)
+    text = open(os.path.join(tmp_path, "vt_0000030.vti")).read().splitlines()
+    assert text[0] == '<?xml version="1.0"?>'
+    assert text[1] == '<VTKFile type="ImageData" version="0.1" byte_order="LittleEndian">'
+    assert text[2] == '  <ImageData WholeExtent="0 16 0 8 0 0" Origin="-1 0 0" Spacing="0.125 0.125 0">'
+    assert text[3] == '  <Piece Extent="0 16 0 8 0 0 ">'
+    names = [l for l in text if "DataArray type" in l]
+    assert [n.split('Name="')[1].split('"')[0] for n in names] == ["rho", "E", "mx", "my"]
+    rho = np.array(text[text.index(names[0]) + 1].split(), dtype=float)
+    np.testing.assert_allclose(rho, U[0][2:-2, 2:-2].ravel(), rtol=1e-5)  # 6 significant digits, like the reference
+
+
+def test_timers_accumulate():
+    hp, _ = both_params("implode", mesh__nx=64, mesh__ny=64)
+    with HydroRun(hp) as hydro:
+        hydro.enable_timers(True)
+        for n in range(4):
+            hydro.godunov_unsplit(n, 1e-4)
+        tm = hydro.timers()
+    assert tm["godunov"] > 0 and tm["fluxes"] > 0 and tm["boundaries"] > 0 and tm["godunov"] >= tm["fluxes"]
+
+
+def test_opt_in_riemann_dispatch_runs():
+    """`riemann=` is dead in the reference; honourRiemannSolver=1 is our opt-in extension. approx/hll must at
+    least stay close to HLLC on a smooth-ish short run (they are different solvers, not parity targets)."""
+    res = {}
+    for solver in ("hllc", "approx", "hll"):
+        hp, _ = both_params("implode", mesh__nx=64, mesh__ny=32, hydro__riemann=solver,
+                            other__honourRiemannSolver="yes", run__nOutput=-1)
+        with HydroRun(hp) as hydro:
+            st = hydro.run(30)
+            res[solver] = hydro.download(HydroRun.U if st.nStep % 2 == 0 else HydroRun.U2)[INNER]
+    for solver in ("approx", "hll"):
+        assert np.isfinite(res[solver]).all()
+        assert np.abs(res[solver][0] - res["hllc"][0]).max() < 0.1
+
+
+def test_errors_are_status_codes():
+    L = e2d.lib()
+    assert L.e2d_compute_dt(None, 0, None, None) == 1
+    p = e2d.Params()
+    assert L.e2d_params_from_ini(b"/nonexistent/file.ini", C.byref(p)) == 2
+    assert (p.nx, p.ny, p.nStepmax) == (2, 2, 1000)  # the reference silently runs these defaults
+    bad = e2d.HydroParams.from_string("[mesh]\nnx=1\nny=1\n")
+    with pytest.raises(e2d.E2dError):
+        HydroRun(bad)
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes: size-independent properties
+@pytest.mark.parametrize("deck,nx,ny,steps", [("blast", 1024, 1536, 20), ("implode", 2048, 2048, 6)])
+def test_large_grid_against_oracle(deck, nx, ny, steps):
+    """configs[1] (blast 1024x1536, HLLC) and the reference's own 2048^2 deck: still small enough for the
+    oracle to follow for a few steps — bit-exact."""
+    hp, op = both_params(deck, mesh__nx=nx, mesh__ny=ny, run__nOutput=-1)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, steps)
+    with HydroRun(hp) as hydro:
+        st = hydro.run(steps)
+        U = hydro.download(HydroRun.U if st.nStep % 2 == 0 else HydroRun.U2)
+    assert st.t == t_ref
+    assert_bitwise(U[INNER], U_ref[INNER], f"{deck} {nx}x{ny}")
+
+
+def test_full_size_8192_properties():
+    """configs[2]: four_quadrant 8192^2.  Too big for the oracle in seconds, so check what must hold at any
+    size: (1) the fused run equals the unfused implementation-0 pipeline bit for bit (two independent code
+    paths), (2) mass is conserved up to what leaves through the absorbing faces in 3 steps (nothing has
+    reached them), (3) the fused CFL reduction equals the stand-alone ComputeDt kernel."""
+    hp, _ = both_params("four_quadrant", mesh__nx=8192, mesh__ny=8192, run__nOutput=-1)
+    with HydroRun(hp) as fused:
+        m0 = fused.download(HydroRun.U)[0][2:-2, 2:-2].sum()
+        st = fused.run(3)
+        Uf = fused.download(HydroRun.U2)
+        dts = fused.dt_history()
+        dt_next = fused.compute_dt(1)
+    m1 = Uf[0][2:-2, 2:-2].sum()
+    assert abs(m1 - m0) / m0 < 1e-12
+    hp0, _ = both_params("four_quadrant", mesh__nx=8192, mesh__ny=8192, run__nOutput=-1)
+    with HydroRun(hp0) as unfused:
+        n, t, dts0 = host_loop(unfused, hp0, 3)
+        U0 = unfused.download(HydroRun.U2)
+        assert unfused.compute_dt(1) == dt_next
+    assert t == st.t
+    assert_bitwise(dts, dts0[1:], "dt")
+    assert_bitwise(Uf[INNER], U0[INNER], "fused vs unfused at 8192^2")
