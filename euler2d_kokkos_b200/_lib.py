@@ -93,7 +93,7 @@ SIGNATURES = {
     "e2d_k_compute_trace_and_fluxes": (C.c_int, [_pp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int,
                                                  C.c_int, _vp]),
     "e2d_k_update_dir": (C.c_int, [_pp, _vp, _vp, C.c_int, C.c_int, _vp]),
-    "e2d_k_fused_step": (C.c_int, [_pp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "e2d_k_fused_step": (C.c_int, [_pp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
     "e2d_k_eval_host": (C.c_int, [_pp, C.c_char_p, _dp, _dp, C.c_long]),
     "e2d_create": (C.c_int, [_pp, C.POINTER(Slab), _vp, _vp, _vp, C.POINTER(_vp)]),
     "e2d_destroy": (C.c_int, [_vp]),

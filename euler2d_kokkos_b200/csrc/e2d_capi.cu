@@ -410,14 +410,14 @@ extern "C"
 
   int
   e2d_k_fused_step(const e2d_params * p, const double * Uin, double * Uout, int jsize_loc, double dt,
-                   const double * d_dt, double * d_invdt, void * stream)
+                   const double * d_dt, double * d_invdt, const int * d_skip, void * stream)
   {
     if (int rc = check_slab_args(p, jsize_loc))
       return rc;
     if (Uin == Uout)
       return fail(E2D_ERR_INVALID, "the fused step is out of place: Uin and Uout must differ");
     E2D_CUDA(launch_fused_step(*p, make_geom(*p, jsize_loc, 0), Uin, Uout, dt, d_dt,
-                               reinterpret_cast<unsigned long long *>(d_invdt), nullptr, (cudaStream_t)stream));
+                               reinterpret_cast<unsigned long long *>(d_invdt), d_skip, (cudaStream_t)stream));
     return E2D_OK;
   }
 

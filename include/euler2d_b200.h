@@ -143,9 +143,11 @@ int e2d_k_update_dir(const e2d_params * p, double * U, const double * F, int dir
  *   d_dt       optional DEVICE pointer to dt (device-resident time loop)
  *   d_invdt    optional DEVICE double (set to 0 by the caller): receives the CFL reduction
  *              (ComputeDtFunctor) of the NEW state, fused in the epilogue
+ *   d_skip     optional DEVICE int: when *d_skip != 0 the launch does nothing (lets a device-resident
+ *              loop run past its own end without a host round trip)
  */
 int e2d_k_fused_step(const e2d_params * p, const double * Uin, double * Uout, int jsize_loc, double dt,
-                     const double * d_dt, double * d_invdt, void * stream);
+                     const double * d_dt, double * d_invdt, const int * d_skip, void * stream);
 
 /* per-cell device functions of HydroBaseFunctor (src/HydroBaseFunctor.h) evaluated on the GPU over
  * n records of HOST doubles — function-level known-answer tests.

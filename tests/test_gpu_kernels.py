@@ -212,7 +212,7 @@ def test_fused_step_exact(deck, nx, ny):
     ref = oracle.godunov(op, U, dt)
     dU, dO = dev(U), dev(np.full_like(U, np.nan))
     acc = torch.zeros(1, dtype=torch.float64, device="cuda")
-    ck(L().e2d_k_fused_step(C.byref(hp.raw), ptr(dU), ptr(dO), op.jsize, dt, None, ptr(acc), None))
+    ck(L().e2d_k_fused_step(C.byref(hp.raw), ptr(dU), ptr(dO), op.jsize, dt, None, ptr(acc), None, None))
     out = host(dO)
     assert_bitwise(out[INNER], ref[INNER], f"fused step {deck} {nx}x{ny}")
     assert host(acc)[0] == oracle.compute_invdt(op, ref), "fused CFL reduction"
@@ -222,14 +222,19 @@ def test_fused_step_exact(deck, nx, ny):
     # device-resident dt gives the same result
     ddt = dev(np.array([dt]))
     dO2 = dev(np.full_like(U, np.nan))
-    ck(L().e2d_k_fused_step(C.byref(hp.raw), ptr(dU), ptr(dO2), op.jsize, 0.0, ptr(ddt), None, None))
+    ck(L().e2d_k_fused_step(C.byref(hp.raw), ptr(dU), ptr(dO2), op.jsize, 0.0, ptr(ddt), None, None, None))
     assert_bitwise(host(dO2)[INNER], ref[INNER], "fused step, dt from device memory")
+    # *d_skip != 0 turns the launch into a no-op
+    skip = torch.ones(1, dtype=torch.int32, device="cuda")
+    dO3 = dev(np.full_like(U, np.nan))
+    ck(L().e2d_k_fused_step(C.byref(hp.raw), ptr(dU), ptr(dO3), op.jsize, dt, None, None, ptr(skip), None))
+    assert np.isnan(host(dO3)).all()
 
 
 def test_fused_step_rejects_in_place(field):
     hp, op, U = field
     d = dev(U)
-    rc = L().e2d_k_fused_step(C.byref(hp.raw), ptr(d), ptr(d), op.jsize, 1e-3, None, None, None)
+    rc = L().e2d_k_fused_step(C.byref(hp.raw), ptr(d), ptr(d), op.jsize, 1e-3, None, None, None, None)
     assert rc == 1 and b"out of place" in L().e2d_last_error()
 
 

@@ -1,0 +1,125 @@
+"""CPU-side checks of the product's host code: the .ini reader (value-identical to the reference incl. float
+truncation), the deck renderer, and that the C-ABI library loads and exports every symbol the header declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import euler2d_kokkos_b200 as e2d
+import oracle
+from euler2d_kokkos_b200 import _lib
+from euler2d_kokkos_b200.decks import DECKS, deck_text
+from util import both_params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("deck", list(DECKS))
+def test_product_parser_equals_oracle_parser(deck):
+    hp, op = both_params(deck)
+    for k, v in op.as_dict().items():
+        assert getattr(hp, k) == v, k
+
+
+def test_float_truncation_and_derived_values():
+    hp = e2d.HydroParams.from_string(deck_text("implode"))
+    assert hp.gamma0 == float.fromhex("0x1.aa7efap+0")        # 1.666 read through strtof
+    assert hp.cfl == float.fromhex("0x1.99999ap-1")
+    assert hp.smallr == float.fromhex("0x1.b7cdfep-34")       # default 1e-10 is a float argument too
+    assert hp.smallp == float.fromhex("0x1.c587529038bb1p-68")
+    assert hp.gamma6 == float.fromhex("0x1.99a955b0f383dp-1")
+    assert (hp.isize, hp.jsize, hp.imax, hp.jmax, hp.ghostWidth) == (260, 132, 259, 131, 2)
+    assert hp.dx == 2.0 ** -7 and hp.implementationVersion == 0 and hp.enableOutput == 1
+    assert hp.outputPrefix == "test_implode" and hp.outputDir == "./"
+
+
+INI_QUIRKS = """
+; comment line
+# another comment
+[RUN]
+TEND = 0.25   ; inline comment needs the blank before the semicolon
+nstepmax=0x20
+noutput=-1
+[mesh]
+nx=12;not-a-comment
+ny = 7
+xmax=2.5
+boundary_type_xmin=3
+[hydro]
+problem=four_quadrant
+riemann=bogus
+gamma0=1.4
+   1.5
+smallr=
+[OTHER]
+implementationVersion=1.9
+"""
+
+
+def test_ini_quirks_match_the_reference_reader(tmp_path):
+    """Case-insensitive keys, hex integers, ';' needs leading whitespace, continuation lines replace the value,
+    empty values fall back to the default, implementationVersion goes float -> int."""
+    hp = e2d.HydroParams.from_string(INI_QUIRKS)
+    f = tmp_path / "q.ini"
+    f.write_text(INI_QUIRKS)
+    op = oracle.params_from_ini(str(f))
+    for k, v in op.as_dict().items():
+        assert getattr(hp, k) == v, k
+    assert hp.tEnd == 0.25 and hp.nStepmax == 32 and hp.enableOutput == 0
+    assert hp.nx == 12 and hp.ny == 7 and hp.boundary_type_xmin == 3
+    assert hp.gamma0 == 1.5                    # the indented line replaced 1.4
+    assert hp.smallr == float.fromhex("0x1.b7cdfep-34")
+    assert hp.riemannSolverType == 0 and hp.implementationVersion == 1
+    hp2 = e2d.HydroParams.from_ini(str(f))     # file path and string path agree
+    assert hp2.raw.as_dict() == hp.raw.as_dict()
+    if oracle.ref_available():                 # and so does the reference's own reader
+        r = oracle.ref_run(str(f), nstep=0, dump=False)["meta"]
+        assert (r["nx"], r["ny"]) == (12, 7) and float.fromhex(r["gamma0_hex"]) == 1.5
+        assert float.fromhex(r["dx_hex"]) == hp.dx and float.fromhex(r["tend_hex"]) == hp.tEnd
+
+
+def test_missing_file_gives_defaults_and_io_status():
+    p = e2d.Params()
+    assert e2d.lib().e2d_params_from_ini(b"/no/such/file.ini", C.byref(p)) == 2
+    assert (p.nx, p.ny, p.nStepmax, p.problemType) == (2, 2, 1000, 0)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "euler2d_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(e2d_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    L = C.CDLL(e2d.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/euler2d_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"euler2d_b200" in e2d.lib().e2d_version() and b"sm_100a" in e2d.lib().e2d_version()
+
+
+def test_struct_layout_matches_the_header():
+    """sizeof(e2d_params) as ctypes sees it must match the C side (checked through a round trip)."""
+    hp = e2d.HydroParams.from_string(deck_text("shocked_bubble"))
+    q = hp.raw.copy()
+    q.nx, q.ny = 100, 50
+    e2d.check(e2d.lib().e2d_params_init(C.byref(q)))
+    assert (q.isize, q.jsize) == (104, 54) and q.dx == (q.xmax - q.xmin) / 100
+    assert q.honourRiemannSolver == 0 and q.outputPrefix == b"test_shocked_bubble"
+    assert q.shock_loc == hp.shock_loc  # fields after the edited ones are intact
+
+
+def test_no_gpu_means_loud_failure():
+    if e2d.lib().e2d_device_count() > 0:
+        pytest.skip("a GPU is present")
+    hp = e2d.HydroParams.from_string(deck_text("implode"))
+    with pytest.raises(e2d.E2dError, match="no CPU fallback"):
+        e2d.HydroRun(hp)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "euler2d_kokkos_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "liboracle" not in text and "euler2d_oracle" not in text, f
