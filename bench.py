@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — the unsplit MUSCL-Hancock Godunov step of euler2d on B200: Mcell-updates/s (fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): the reference's four_quadrant deck scaled to 8192 x 8192 cells per GPU
+(BASELINE.json configs[2], the size north_star quotes the roofline target on); with N GPUs the domain is
+8192 x (8192*N) cut into N y-slabs (weak scaling).  One "step" = compute_dt + make_boundaries +
+godunov_unsplit for every cell.  Inputs are the deck's analytic initial condition (synthetic, no RNG); the
+state (2.1 GB per array) is far larger than the 126 MB L2, so no L2 flush is needed between steps.
+
+  value   device-resident loop, state already in HBM, CUDA events on the launching stream, max over ranks
+  e2e     the same metric through the host-buffer entry point (e2d_step_host): every step copies the
+          whole state host->device from pinned memory, steps, and copies it back
+  roofline  fused step kernel alone: 64 B/cell (read + write 4 doubles) / its mean launch time, against the
+            measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the reference's own sources (oracle/_ref) on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX_PER_GPU = 8192
+NY_PER_GPU = 8192
+ALGO_BYTES_PER_CELL = 64  # 4 doubles read + 4 doubles written per cell update
+METRIC = "Mcell-updates/s (fp64)"
+UNIT = "Mcell-updates/s"
+
+
+def workload_overrides(n_gpus: int, nx=NX_PER_GPU, ny=NY_PER_GPU):
+    # keep dx == dy when the domain is stretched in y for weak scaling
+    return dict(mesh__nx=nx, mesh__ny=ny * n_gpus, mesh__ymax=float(n_gpus), run__nOutput=-1,
+                run__nStepmax=10 ** 8, run__tEnd=1e9)
+
+
+def config_dict(n_gpus: int):
+    return {"workload": f"four_quadrant {NX_PER_GPU}x{NY_PER_GPU * n_gpus} fp64 (test_four_quadrant.ini scaled; "
+                        f"{NX_PER_GPU}x{NY_PER_GPU} cells per GPU, y-slab split), HLLC, slope_type 2, fused step",
+            "cells_per_gpu": NX_PER_GPU * NY_PER_GPU, "parallelism": f"y-slab x{n_gpus}",
+            "l2_policy": "state (2.1 GB/array/GPU) >> L2 (126 MB): no flush between steps",
+            "build": "strict fp64 (-fmad=false), bit-identical to the reference"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference_sample(nx: int, ny: int, steps: int, warmup: int, threads: int | None = None):
+    """Time the reference's own sources (oracle/_ref/ref_dump) on the host cores."""
+    import oracle
+    from euler2d_kokkos_b200.decks import write_deck
+
+    if not oracle.ref_available():
+        oracle.build()
+    exe = oracle.ref_binary()
+    kind = "reference"
+    if not os.path.exists(exe):
+        return None
+    threads = threads or os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as td:
+        ini = write_deck(os.path.join(td, "ref.ini"), "four_quadrant", **workload_overrides(1, nx, ny))
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="threads")
+        t0 = time.perf_counter()
+        out = subprocess.run([exe, ini, "--nstep", str(steps + warmup), "--warmup", str(warmup)], check=True,
+                             capture_output=True, text=True, env=env).stdout
+        wall = time.perf_counter() - t0
+    meta = json.loads(out.strip().splitlines()[-1])
+    return {"value": meta["mcell_updates_per_s"], "unit": UNIT, "cores": int(meta.get("threads", threads)),
+            "kind": kind, "sample": f"four_quadrant {nx}x{ny}, {meta['timed_steps']} timed steps after {warmup} "
+                                    f"warm-up, impl 0, OMP_NUM_THREADS={threads} ({os.path.basename(exe)})",
+            "loop_seconds": meta["loop_seconds"], "wall_seconds": round(wall, 2), "timed_steps": meta["timed_steps"]}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # bounded sample: 2048^2 cells per step keeps W+K steps within minutes on any host
+    nx = ny = 2048
+    res = run_reference_sample(nx, ny, args.steps, args.warmup)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dump missing and /root/reference absent"}))
+        return 0
+    ms = res["loop_seconds"] / max(res["timed_steps"], 1) * 1e3
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+            "impl": "reference",
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "each step is a bounded sample (2048x2048 cells) of the workload; Mcell-updates/s is size "
+                    "independent beyond cache"}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import euler2d_kokkos_b200 as e2d
+    from euler2d_kokkos_b200.decks import deck_text
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world != 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if e2d.lib().e2d_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — euler2d_kokkos_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, W = args.steps, max(args.warmup, 3)
+    hp = e2d.HydroParams.from_string(deck_text("four_quadrant", **workload_overrides(world)))
+    cells_total = hp.nx * hp.ny
+    launches0 = e2d.lib().e2d_kernel_launch_count()
+    extra = {}
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if not distributed:
+        hydro = e2d.HydroRun(hp)
+        hydro.enable_timers(True)  # one event pair around each fused-step launch (no extra syncs)
+        hydro.run(W)
+        barrier()
+        launches0 = e2d.lib().e2d_kernel_launch_count()
+        with ClockSampler(local_rank) as clk:
+            st = hydro.run(W + K)
+        barrier()
+        seconds = st.seconds
+        kernel_seconds = st.seconds_step_kernel
+        launches = e2d.lib().e2d_kernel_launch_count() - launches0
+        assert st.nStep == W + K
+    else:
+        from euler2d_kokkos_b200.distributed import SlabRun
+
+        run = SlabRun(hp, device=dev)
+        for _ in range(W):
+            run.step()
+        barrier()
+        launches0 = e2d.lib().e2d_kernel_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            ev0.record()
+            for _ in range(K):
+                run.step()
+            ev1.record()
+            barrier()
+        seconds = ev0.elapsed_time(ev1) * 1e-3
+        kernel_seconds = 0.0
+        launches = e2d.lib().e2d_kernel_launch_count() - launches0
+        tmax = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        seconds = float(tmax.item())
+        assert run.nStep == W + K
+
+    value = cells_total * K / seconds * 1e-6
+
+    # ---------------- roofline of the dominant kernel (fused step), measured live
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    roofline = None
+    if kernel_seconds > 0:
+        per_launch = kernel_seconds / K
+        achieved = ALGO_BYTES_PER_CELL * (hp.nx * hp.ny) / per_launch * 1e-9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_fused_step_8192x8192")
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                    "traffic": traffic, "kernel": "k_fused_step<HLLC, fused dt>", "kernel_ms_per_launch": per_launch * 1e3,
+                    "kernel_share_of_step": kernel_seconds / seconds, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * hp.nx * hp.ny,
+                    "note": "the strict fp64 step is FP64-issue bound, not HBM bound (DESIGN.md §4): ~700 FP64-pipe "
+                            "instructions per cell vs 64 B"}
+
+    # ---------------- e2e through the host-buffer entry point (rank-local slab; N=1 only for now)
+    e2e = None
+    cpu_baseline = None
+    if not distributed:
+        n_e2e = max(1, min(K, 5))
+        nbytes = 4 * hp.jsize * hp.isize * 8
+        h_in = torch.empty(4 * hp.jsize * hp.isize, dtype=torch.float64).pin_memory()
+        h_out = torch.empty_like(h_in).pin_memory()
+        cur = e2d.E2D_U if (W + K) % 2 == 0 else e2d.E2D_U2
+        e2d.check(e2d.lib().e2d_download(hydro._h, cur, h_in.data_ptr(), e2d.LAYOUT_SOA))
+        hydro.step_host_ptr(h_in.data_ptr(), h_out.data_ptr())  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            hydro.step_host_ptr(h_in.data_ptr(), h_out.data_ptr())
+            h_in, h_out = h_out, h_in
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": cells_total * n_e2e / t_e2e * 1e-6, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": n_e2e, "ms_per_step": t_e2e / n_e2e * 1e3,
+               "api": "e2d_step_host (pinned host buffers): H2D state, boundaries, dt, fused step, D2H state"}
+        hydro.close()
+        del hydro
+        if rank == 0 and not args.no_cpu_baseline:
+            try:
+                cpu_baseline = run_reference_sample(4096, 4096, 6, 1)
+                if cpu_baseline:
+                    cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as ex:  # never lose the GPU number to a CPU-side problem
+                cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": seconds / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config_dict(world), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+                "hbm_gbs_algorithmic": ALGO_BYTES_PER_CELL * cells_total * K / seconds * 1e-9, "impl": "ours"}
+        line.update(extra)
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

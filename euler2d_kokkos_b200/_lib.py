@@ -66,7 +66,7 @@ class Slab(C.Structure):
 
 class RunStats(C.Structure):
     _fields_ = [("nStep", C.c_int), ("t", C.c_double), ("dt_last", C.c_double), ("seconds", C.c_double),
-                ("launches", C.c_longlong)]
+                ("launches", C.c_longlong), ("seconds_step_kernel", C.c_double)]
 
 
 # every symbol include/euler2d_b200.h declares: name -> (restype, argtypes)

@@ -85,6 +85,7 @@ struct e2d_handle
   double      timers[5] = { 0, 0, 0, 0, 0 };
   cudaEvent_t ev[2] = { nullptr, nullptr };
   cudaEvent_t ev_t[5][2] = {}; // one event pair per timer: the godunov timer nests the others
+  std::vector<cudaEvent_t> ev_step; // e2d_run profiling: one pair per step of a batch
 };
 
 namespace
@@ -582,6 +583,9 @@ extern "C"
       for (int e = 0; e < 2; ++e)
         if (h->ev_t[k][e])
           cudaEventDestroy(h->ev_t[k][e]);
+    for (auto & e : h->ev_step)
+      if (e)
+        cudaEventDestroy(e);
     if (h->own_stream && h->stream)
       cudaStreamDestroy(h->stream);
     delete h;
@@ -682,6 +686,13 @@ extern "C"
     E2D_CUDA(cudaEventRecord(h->ev[0], st));
     int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when kernels no-op
     const int batch = 64;
+    double    step_kernel_ms = 0.0;
+    if (h->timing && h->ev_step.empty())
+    {
+      h->ev_step.resize(2 * batch, nullptr);
+      for (auto & e : h->ev_step)
+        E2D_CUDA(cudaEventCreate(&e));
+    }
     bool      finished = h->h_loop->done != 0;
     while (!finished)
     {
@@ -694,12 +705,23 @@ extern "C"
         double * out = (n_host % 2 == 0) ? h->U2 : h->U;
         E2D_CUDA(launch_loop_begin_step(h->d_loop, p.cfl, p.tEnd, st));
         E2D_CUDA(launch_make_boundaries(p, h->g, in, E2D_FACES_ALL, &h->d_loop->done, st));
+        if (h->timing)
+          E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
         E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_loop->dt, &h->d_loop->invdt_next,
                                    &h->d_loop->done, st));
+        if (h->timing)
+          E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));
         E2D_CUDA(launch_loop_end_step(h->d_loop, p.tEnd, (int)max_steps, h->d_hist, h->hist_cap, st));
       }
       E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
       E2D_CUDA(cudaStreamSynchronize(st));
+      if (h->timing)
+        for (long k = 0; k < todo; ++k)
+        {
+          float ms_k = 0;
+          E2D_CUDA(cudaEventElapsedTime(&ms_k, h->ev_step[2 * k], h->ev_step[2 * k + 1]));
+          step_kernel_ms += ms_k;
+        }
       finished = h->h_loop->done != 0 || n_host >= max_steps;
     }
     E2D_CUDA(cudaEventRecord(h->ev[1], st));
@@ -718,6 +740,7 @@ extern "C"
       stats->dt_last = h->dt_last;
       stats->seconds = ms * 1e-3;
       stats->launches = (long long)(g_launches.load() - launches0);
+      stats->seconds_step_kernel = step_kernel_ms * 1e-3;
     }
     return E2D_OK;
   }

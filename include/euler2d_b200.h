@@ -206,6 +206,9 @@ typedef struct e2d_run_stats
   double dt_last;      /* dt of the last step */
   double seconds;      /* device time of this call's steps (CUDA events on the handle's stream) */
   long long launches;  /* kernels launched by this call */
+  double seconds_step_kernel; /* device time spent inside the fused step kernel alone (sum over its launches,
+                                 one CUDA-event pair per launch on the handle's stream); 0 unless
+                                 e2d_enable_timers(h, 1) */
 } e2d_run_stats;
 
 /* The main loop of src/main.cpp:100-143 with IO off, device-resident: dt, t and nStep live in

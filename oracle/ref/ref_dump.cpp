@@ -3,7 +3,8 @@
 // dumps the conservative state raw (the reference's VTK writer keeps 6 digits only,
 // SURVEY.md §8c trap 3) and can time the solver loop for the CPU baseline.
 //
-// usage: ref_dump <file.ini> [--out PREFIX] [--nstep N] [--quiet] [--states K]
+// usage: ref_dump <file.ini> [--out PREFIX] [--nstep N] [--warmup W] [--states K]
+//   --warmup W     the loop timer starts after W steps (bench.py's reference arm)
 //   PREFIX.U.bin   final state, doubles, [var][j][i] (whole array incl. ghost cells)
 //   PREFIX.dt.bin  dt used at every step (doubles, nStep entries) preceded by the dt of main.cpp:87
 //   PREFIX.sN.bin  (with --states K) state after every K-th step, same layout
@@ -11,6 +12,9 @@
 //
 // Builds against the real Kokkos or against oracle/kokkos_shim (same source).
 #include <chrono>
+#ifdef _OPENMP
+#  include <omp.h>
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +62,7 @@ main(int argc, char * argv[])
     std::string ini = argv[1], out;
     long        nstep_override = -1;
     int         states_every = 0;
+    int         warmup = 0;
     for (int a = 2; a < argc; ++a)
     {
       if (!strcmp(argv[a], "--out") && a + 1 < argc)
@@ -66,6 +71,8 @@ main(int argc, char * argv[])
         nstep_override = atol(argv[++a]);
       else if (!strcmp(argv[a], "--states") && a + 1 < argc)
         states_every = atoi(argv[++a]);
+      else if (!strcmp(argv[a], "--warmup") && a + 1 < argc)
+        warmup = atoi(argv[++a]);
     }
 
     ConfigMap            configMap(ini);
@@ -90,6 +97,8 @@ main(int argc, char * argv[])
     auto t0 = std::chrono::steady_clock::now();
     while (t < params.tEnd && nStep < params.nStepmax) // main.cpp:100
     {
+      if (nStep == warmup)
+        t0 = std::chrono::steady_clock::now();
       dt = hydro->compute_dt(nStep % 2); // main.cpp:128
       if (t + dt > params.tEnd)          // main.cpp:131-134
         dt = params.tEnd - t;
@@ -110,6 +119,7 @@ main(int argc, char * argv[])
       fwrite(dts.data(), sizeof(real_t), dts.size(), f);
       fclose(f);
     }
+    const int    timed_steps = nStep - (warmup < nStep ? warmup : 0);
     const double cells_ghost = 1.0 * params.isize * params.jsize;
     const double cells = 1.0 * params.nx * params.ny;
     printf("{\"nstep\": %d, \"t_hex\": \"%a\", \"t\": %.17g, \"isize\": %d, \"jsize\": %d, "
@@ -117,7 +127,7 @@ main(int argc, char * argv[])
            "\"mcell_updates_per_s_ref_style\": %.4f, \"dx_hex\": \"%a\", \"dy_hex\": \"%a\", "
            "\"gamma0_hex\": \"%a\", \"cfl_hex\": \"%a\", \"smallr_hex\": \"%a\", \"smallc_hex\": \"%a\", "
            "\"smallp_hex\": \"%a\", \"smallpp_hex\": \"%a\", \"gamma6_hex\": \"%a\", \"tend_hex\": \"%a\", "
-           "\"impl\": %d}\n",
+           "\"impl\": %d, \"timed_steps\": %d, \"threads\": %d}\n",
            nStep,
            t,
            t,
@@ -126,8 +136,8 @@ main(int argc, char * argv[])
            params.nx,
            params.ny,
            secs,
-           secs > 0 ? nStep * cells / secs * 1e-6 : 0.0,
-           secs > 0 ? nStep * cells_ghost / secs * 1e-6 : 0.0,
+           secs > 0 ? timed_steps * cells / secs * 1e-6 : 0.0,
+           secs > 0 ? timed_steps * cells_ghost / secs * 1e-6 : 0.0,
            params.dx,
            params.dy,
            params.settings.gamma0,
@@ -138,7 +148,14 @@ main(int argc, char * argv[])
            params.settings.smallpp,
            params.settings.gamma6,
            params.tEnd,
-           params.implementationVersion);
+           params.implementationVersion,
+           timed_steps,
+#ifdef _OPENMP
+           omp_get_max_threads()
+#else
+           1
+#endif
+    );
     delete hydro;
   }
   Kokkos::finalize();
