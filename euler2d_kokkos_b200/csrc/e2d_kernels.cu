@@ -15,7 +15,7 @@ namespace
 {
 
 constexpr int kBX = 128;       // threads per block of the marching kernel (= columns incl. 4 halo columns)
-constexpr int kMarchMinBlocks = 3;
+constexpr int kMarchMinBlocks = 4;
 
 __host__ __device__ __forceinline__ size_t
 cell(const Geom & g, int i, int j, int v)
@@ -898,6 +898,7 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   a.isize = g.isize;
   a.jsize = g.jsize;
   a.s = make_settings(p);
+  a.c = make_step_consts(a.s);
   a.dt = dt;
   a.d_dt = d_dt;
   a.invdt_bits = d_invdt_bits;

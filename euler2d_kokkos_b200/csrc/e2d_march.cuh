@@ -1,15 +1,17 @@
 // The fused step as a row-marching ("2.5-D") kernel body.
 //
-// One thread owns one grid column i and marches along +j through a segment of rows, keeping a
-// three-row window of primitive variables in registers.  Per row it
-//   A) fetches the west/east primitives of the row from shared memory, limits the slopes, does the
-//      MUSCL-Hancock half-step trace to the four faces of its cell, solves the y-face Riemann problem
-//      against the YMAX state it kept from the previous row, and publishes its XMAX face state and the
-//      next row's primitives;
+// One thread owns one grid column i and marches along +j through a segment of rows.  Per row r:
+//   A) reads the primitives of the five-point stencil from a three-row ring in shared memory,
+//      limits the slopes, does the MUSCL-Hancock half-step trace to the four faces of cell (i, r),
+//      publishes the XMAX face state (for the east neighbour) and parks the YMAX face state (for
+//      its own next row);
 //   -- one __syncthreads --
-//   B) solves the x-face Riemann problem against the XMAX state of its west neighbour, publishes the
-//      x flux, completes the conservative update of the PREVIOUS row (whose east x flux and north y
-//      flux are now known), stores it, and folds the next step's CFL reduction into the same pass.
+//   B) solves the x-face Riemann problem (west face of (i, r)) and the y-face one (south face) back
+//      to back in one straight-line block, so the two solves, the CFL integrand of the row being
+//      completed and the primitive conversion of the row being fetched overlap in the FP64 pipe;
+//      publishes the x flux, completes the conservative update of row r-1 (its east x flux and
+//      north y flux are now known), stores it, folds the next step's CFL reduction in, and
+//      converts row r+2 (loaded at the top of the phase) to primitives into the ring.
 //
 // Each cell's slopes and trace are computed exactly once, each face's Riemann problem exactly once
 // (the reference's flux kernel computes 3 slope sets, 4 traces and 2 solves per cell,
@@ -18,10 +20,19 @@
 // order of UpdateFunctor (src/HydroRunFunctors.h:695-713) with fluxes pre-scaled by dt/dx, dt/dy
 // (:572-575,:637-640), so the result is bit-identical to the reference's implementation 0.
 //
-// Shared memory is double-buffered on the row parity, which is what allows a single barrier per row:
-//   buffer[r&1].Q    primitives of row r+1      written in A(r)   read in A(r+1)
-//   buffer[r&1].XMAX XMAX face states of row r  written in A(r)   read in B(r)
-//   buffer[r&1].FX   x fluxes of row r-1        written in B(r-1) read in B(r)
+// Shared memory (ring slots are row % 3 or row & 1; one barrier per row suffices):
+//   Q[r%3]       primitives of rows r-1, r, r+1      written in B(r-2)   read in A(r-1..r+1)
+//   RY[r%3]      refined 1/rho of the same rows      own column only
+//   U[r&1]       conservatives of rows r, r+1        own column only     written B(r-2), read B(r)
+//   XMAX[r&1]    XMAX face states of row r           written in A(r)     read in B(r) by the east lane
+//   YMAX[r&1]    YMAX face states of row r           own column only     written A(r), read B(r+1)
+//   FX[(r+1)&1]  x fluxes of row r                   written in B(r)     read in B(r+1) by the west lane
+// Keeping the own-column rows in shared memory instead of registers is what brings the kernel under
+// 128 registers (4 blocks of 128 threads per SM instead of 3).
+//
+// All work is unconditional (rows outside [j0, j1) compute on valid-but-unused data); only the side
+// effects are predicated.  The arithmetic is the lean-but-exact form of e2d_lean.cuh; when a fast-path
+// guard fails anywhere in a phase the phase is recomputed with plain IEEE operators.
 //
 // The body is written as a per-thread state machine (init / phaseA / phaseB) so that the test-suite
 // can run the very same code on the host, one "thread" after the other with the barrier between the
@@ -29,7 +40,7 @@
 #ifndef E2D_MARCH_CUH
 #define E2D_MARCH_CUH
 
-#include "e2d_math.cuh"
+#include "e2d_lean.cuh"
 
 namespace e2d
 {
@@ -41,6 +52,7 @@ struct MarchArgs
   int                  isize, jsize; // slab extent incl. ghosts
   int                  seg_rows;     // interior rows per block segment
   Settings             s;
+  StepConsts           c;
   double               dt;         // used when d_dt == nullptr
   const double *       d_dt;       // device-resident dt (optional)
   unsigned long long * invdt_bits; // optional: atomicMax target for the next step's CFL reduction
@@ -49,8 +61,11 @@ struct MarchArgs
 template <int BX>
 struct MarchSmem
 {
-  double Q[2][4][BX];
+  double Q[3][4][BX];
+  double RY[3][BX];
+  double U[2][4][BX];
   double XMAX[2][4][BX];
+  double YMAX[2][4][BX];
   double FX[2][4][BX];
 };
 
@@ -70,13 +85,12 @@ struct MarchThread
   bool   store;     // this thread owns an output column
   size_t plane;     // isize * jsize
   double dtdx, dtdy;
-  // carried across rows
-  double qS[4], qC[4], qN[4]; // primitives of rows r-1, r, r+1
-  double uC[4], uN[4];        // conservatives of rows r, r+1
-  double xminC[4];            // XMIN face state of row r (A -> B)
-  double ymaxP[4];            // YMAX face state of row r-1
-  double fyP[4], fyN[4];      // y fluxes at the south faces of rows r-1 and r
-  double pend[4];             // U(r-1) + Fx(i, r-1)
+  Recip  rdx, rdy; // dx, dy and their refined reciprocals (CFL integrand)
+  int    m3;       // (row being traced) % 3
+  // carried across the barrier / rows
+  double xmin[4], ymin[4]; // XMIN / YMIN face states of row r (A -> B)
+  double fyP[4];           // y flux at the south face of row r-1
+  double pend[4];          // U(r-1) + Fx(i, r-1)
   double invdt;
 
   E2D_HD void
@@ -88,10 +102,36 @@ struct MarchThread
       u[v] = p[v * plane];
   }
 
+  // conservative -> primitive of one cell of a fetched row, into ring slot `slot`
   E2D_HD void
-  to_prim(const MarchArgs & a, const double u[4], double q[4]) const
+  convert_into(const MarchArgs & a, MarchSmem<BX> & sm, const double u[4], int slot) const
   {
-    compute_primitives_noc(a.s, u[ID], u[IP], u[IU], u[IV], q[ID], q[IP], q[IU], q[IV]);
+    double q[4];
+    Recip  rd;
+    bool   ok = true;
+    prim_lean<true>(a.s, a.c, u, q, rd, ok);
+    if (!ok)
+    {
+      Recip unused;
+      prim_lean<false>(a.s, a.c, u, q, unused, ok);
+    }
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+      sm.Q[slot][v][t] = q[v];
+    sm.RY[slot][t] = rd.y;
+  }
+
+  template <bool LEAN>
+  E2D_HD void
+  solve(const MarchArgs & a, const double l[4], const double r[4], int in, int it, double f[4], bool & ok) const
+  {
+    // in / it: index of the normal / transverse velocity (IU, IV for x faces; swapped for y faces,
+    // src/HydroRunFunctors.h:628-632)
+    if (SOLVER == 2)
+      hllc_lean<LEAN>(a.s, a.c, l[ID], l[IP], l[in], l[it], r[ID], r[IP], r[in], r[it], f[ID], f[IP], f[in], f[it],
+                      ok);
+    else
+      riemann<SOLVER>(a.s, l[ID], l[IP], l[in], l[it], r[ID], r[IP], r[in], r[it], f[ID], f[IP], f[in], f[it]);
   }
 
   // returns false when the block has no rows to produce (uniform over the block)
@@ -114,22 +154,30 @@ struct MarchThread
     const double dt = a.d_dt ? *a.d_dt : a.dt;
     dtdx = dt / a.s.dx; // HydroRun.h:290-291
     dtdy = dt / a.s.dy;
+    bool unused = true;
+    rdx = recip_of<true, false>(a.s.dx, unused);
+    rdy = recip_of<true, false>(a.s.dy, unused);
     invdt = 0.0;
+    m3 = (j0 - 1) % 3;
 
+    // rows j0-2, j0-1, j0 -> primitive ring; rows j0-1, j0 -> conservative ring
     double u[4];
     load_row(a, j0 - 2, u);
-    to_prim(a, u, qS);
-    load_row(a, j0 - 1, uC);
-    to_prim(a, uC, qC);
-    load_row(a, j0, uN);
-    to_prim(a, uN, qN);
+    convert_into(a, sm, u, (j0 - 2) % 3);
+    load_row(a, j0 - 1, u);
+    convert_into(a, sm, u, (j0 - 1) % 3);
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+      sm.U[(j0 - 1) & 1][v][t] = u[v];
+    load_row(a, j0, u);
+    convert_into(a, sm, u, j0 % 3);
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      sm.Q[(j0 - 2) & 1][v][t] = qC[v]; // primitives of the first traced row, r = j0-1
-      ymaxP[v] = 0.0;
+      sm.U[j0 & 1][v][t] = u[v];
+      sm.YMAX[(j0 - 2) & 1][v][t] = u[v]; // any valid state: the south face of row j0-1 is solved but unused
+      sm.FX[(j0 - 1) & 1][v][t] = 0.0;    // read (and unused) by the first phase B
       fyP[v] = 0.0;
-      fyN[v] = 0.0;
       pend[v] = 0.0;
     }
     return true;
@@ -140,116 +188,125 @@ struct MarchThread
   phaseA(const MarchArgs & a, MarchSmem<BX> & sm, int r)
   {
     const Settings & s = a.s;
-    double           qW[4], qE[4], dqX[4], dqY[4], s0[4], xmax[4], ymin[4], ymax[4];
+    const int        sC = m3, sS = (m3 == 0) ? 2 : m3 - 1, sN = (m3 == 2) ? 0 : m3 + 1;
+    double           qC[4], qW[4], qE[4], qS[4], qN[4], dqX[4], dqY[4], s0[4], xmax[4], ymax[4];
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      qW[v] = sm.Q[(r - 1) & 1][v][tm];
-      qE[v] = sm.Q[(r - 1) & 1][v][tp];
+      qC[v] = sm.Q[sC][v][t];
+      qW[v] = sm.Q[sC][v][tm];
+      qE[v] = sm.Q[sC][v][tp];
+      qS[v] = sm.Q[sS][v][t];
+      qN[v] = sm.Q[sN][v][t];
     }
-    slopes_dir(s, qC, qE, qW, dqX);
-    slopes_dir(s, qC, qN, qS, dqY);
-    trace_sources(s, qC, dqX, dqY, s0);
-    trace_face<-1>(s, qC, dqX, s0, dtdx, xminC);
+    Recip rd;
+    rd.d = qC[ID];
+    rd.y = sm.RY[sC][t];
+
+    // slope_unsplit_hydro_2d (src/HydroBaseFunctor.h:473-516): slope_type outside {1,2} -> zero slopes
+    const bool limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
+    slopes_lean(s.slope_type, limited, qC, qE, qW, dqX);
+    slopes_lean(s.slope_type, limited, qC, qN, qS, dqY);
+
+    bool ok = true;
+    trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
+    if (!ok)
+      trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
+    trace_face<-1>(s, qC, dqX, s0, dtdx, xmin);
     trace_face<+1>(s, qC, dqX, s0, dtdx, xmax);
     trace_face<-1>(s, qC, dqY, s0, dtdy, ymin);
     trace_face<+1>(s, qC, dqY, s0, dtdy, ymax);
 
-    if (r >= j0)
-    {
-      // south face of row r: left = YMAX of row r-1, right = YMIN of row r, IU<->IV swapped
-      // (HydroRunFunctors.h:621-640)
-      double f_d, f_e, f_n, f_t;
-      riemann<SOLVER>(s, ymaxP[ID], ymaxP[IP], ymaxP[IV], ymaxP[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU],
-                      f_d, f_e, f_n, f_t);
-      fyN[ID] = f_d * dtdy;
-      fyN[IP] = f_e * dtdy;
-      fyN[IU] = f_t * dtdy;
-      fyN[IV] = f_n * dtdy;
-    }
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
       sm.XMAX[r & 1][v][t] = xmax[v];
-      sm.Q[r & 1][v][t] = qN[v];
-      ymaxP[v] = ymax[v];
+      sm.YMAX[r & 1][v][t] = ymax[v];
     }
+  }
+
+  // everything of phase B that is arithmetic: the two face solves, the update of row r-1 and its CFL integrand
+  template <bool LEAN>
+  E2D_HD void
+  compute_B(const MarchArgs & a, const double xl[4], const double yl[4], const double fxE[4], double fx[4], double fy[4], double un[4], double & cflv, bool & ok) const
+  {
+    // west face of cell (i, r): left = XMAX of (i-1, r), right = XMIN of (i, r) (HydroRunFunctors.h:559-575)
+    solve<LEAN>(a, xl, xmin, IU, IV, fx, ok);
+    // south face of row r: left = YMAX of row r-1, right = YMIN of row r, IU<->IV swapped (:621-640)
+    solve<LEAN>(a, yl, ymin, IV, IU, fy, ok);
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+    {
+      fx[v] = fx[v] * dtdx;
+      fy[v] = fy[v] * dtdy;
+    }
+    // complete row r-1: UpdateFunctor order (HydroRunFunctors.h:695-713)
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+    {
+      double x = pend[v]; // U + Fx(i, j)
+      x -= fxE[v];        //   - Fx(i+1, j)
+      x += fyP[v];        //   + Fy(i, j)
+      x -= fy[v];         //   - Fy(i, j+1)
+      un[v] = x;
+    }
+    cflv = 0.0;
+    if (FUSE_DT)
+      cflv = cfl_lean<LEAN>(a.s, a.c, rdx, rdy, un, ok);
   }
 
   E2D_HD void
   phaseB(const MarchArgs & a, MarchSmem<BX> & sm, int r)
   {
-    const Settings & s = a.s;
-    double           uP[4];
-    const bool       more = r < j1;
-    if (more)
-      load_row(a, r + 2, uP); // issued early, consumed at the bottom
-
-    double     fx[4] = { 0.0, 0.0, 0.0, 0.0 };
-    const bool xface = (r >= j0) && (r < j1);
-    if (xface)
+    // fetch row r+2 (clamped: the last fetch of the topmost segment is a harmless repeat), consumed at the bottom
+    double uP[4];
     {
-      // west face of cell (i, r): left = XMAX of (i-1, r), right = XMIN of (i, r)
-      // (HydroRunFunctors.h:559-575)
-      double xl[4];
-      E2D_UNROLL
-      for (int v = 0; v < 4; ++v)
-        xl[v] = sm.XMAX[r & 1][v][tm];
-      double f_d, f_e, f_n, f_t;
-      riemann<SOLVER>(s, xl[ID], xl[IP], xl[IU], xl[IV], xminC[ID], xminC[IP], xminC[IU], xminC[IV], f_d, f_e,
-                      f_n, f_t);
-      fx[ID] = f_d * dtdx;
-      fx[IP] = f_e * dtdx;
-      fx[IU] = f_n * dtdx;
-      fx[IV] = f_t * dtdx;
-      E2D_UNROLL
-      for (int v = 0; v < 4; ++v)
-        sm.FX[(r + 1) & 1][v][t] = fx[v];
+      const int jn = (r + 2 < a.jsize) ? r + 2 : a.jsize - 1;
+      load_row(a, jn, uP);
     }
 
-    if (r >= j0 + 1)
+    double xl[4], yl[4], fxE[4], uC[4], fx[4], fy[4], un[4], cflv;
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
     {
-      // complete row r-1: UpdateFunctor order (HydroRunFunctors.h:695-713)
-      double un[4];
+      xl[v] = sm.XMAX[r & 1][v][tm];
+      yl[v] = sm.YMAX[(r - 1) & 1][v][t];
+      fxE[v] = sm.FX[r & 1][v][tp];
+      uC[v] = sm.U[r & 1][v][t];
+    }
+    bool ok = true;
+    compute_B<true>(a, xl, yl, fxE, fx, fy, un, cflv, ok);
+    if (!ok)
+      compute_B<false>(a, xl, yl, fxE, fx, fy, un, cflv, ok);
+
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+      sm.FX[(r + 1) & 1][v][t] = fx[v];
+
+    if (store && r >= j0 + 1)
+    {
+      double * po = a.Uout + (size_t)(r - 1) * a.isize + i;
       E2D_UNROLL
       for (int v = 0; v < 4; ++v)
-      {
-        double x = pend[v];           // U + Fx(i, j)
-        x -= sm.FX[r & 1][v][tp];     //   - Fx(i+1, j)
-        x += fyP[v];                  //   + Fy(i, j)
-        x -= fyN[v];                  //   - Fy(i, j+1)
-        un[v] = x;
-      }
-      if (store)
-      {
-        double * po = a.Uout + (size_t)(r - 1) * a.isize + i;
-        E2D_UNROLL
-        for (int v = 0; v < 4; ++v)
-          po[v * plane] = un[v];
-        if (FUSE_DT)
-          invdt = fmax(invdt, cfl_inv_dt(s, un[ID], un[IP], un[IU], un[IV]));
-      }
+        po[v * plane] = un[v];
+      if (FUSE_DT)
+        invdt = fmax(invdt, cflv); // fmax drops a NaN operand like the reference's reduction (:72)
     }
 
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      if (xface)
-        pend[v] = uC[v] + fx[v];
-      fyP[v] = fyN[v];
+      pend[v] = uC[v] + fx[v];
+      fyP[v] = fy[v];
     }
-    if (more)
-    {
-      E2D_UNROLL
-      for (int v = 0; v < 4; ++v)
-      {
-        qS[v] = qC[v];
-        qC[v] = qN[v];
-        uC[v] = uN[v];
-        uN[v] = uP[v];
-      }
-      to_prim(a, uP, qN);
-    }
+
+    // row r+2 -> rings (slot of row r-1 in Q/RY, slot of row r in U: both consumed above / in A(r))
+    const int sS = (m3 == 0) ? 2 : m3 - 1;
+    convert_into(a, sm, uP, sS);
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+      sm.U[r & 1][v][t] = uP[v];
+    m3 = (m3 == 2) ? 0 : m3 + 1;
   }
 };
 

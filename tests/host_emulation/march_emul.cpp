@@ -41,6 +41,7 @@ run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_lo
   a.jsize = jsize_loc;
   a.seg_rows = seg_rows;
   a.s = settings_of(p);
+  a.c = make_step_consts(a.s);
   a.dt = dt;
   a.d_dt = nullptr;
   a.invdt_bits = nullptr;
