@@ -432,7 +432,8 @@ extern "C"
       const char * name;
       int          id, nin, nout;
     } table[] = { { "prim", 0, 4, 5 },   { "slope", 1, 20, 8 }, { "trace", 2, 14, 16 }, { "hllc", 3, 8, 4 },
-                  { "approx", 4, 8, 8 }, { "cmpflx", 5, 4, 4 }, { "hll", 6, 8, 4 } };
+                  { "approx", 4, 8, 8 }, { "cmpflx", 5, 4, 4 }, { "hll", 6, 8, 4 },     { "hllc_lean", 7, 8, 5 },
+                  { "cell_lean", 8, 4, 6 }, { "trace_lean", 9, 22, 25 }, { "div", 10, 2, 5 }, { "sqrt", 11, 1, 3 } };
     int id = -1, nin = 0, nout = 0;
     for (const auto & e : table)
       if (!std::strcmp(e.name, func))

@@ -6,7 +6,7 @@
 #include <cstdio>
 
 #include "e2d_internal.h"
-#include "e2d_march.cuh"
+#include "e2d_march.cuh" // includes e2d_lean.cuh
 
 namespace e2d
 {
@@ -509,7 +509,8 @@ k_fused_step(MarchArgs a, const int * __restrict__ d_done)
 {
   if (d_done && *d_done)
     return;
-  __shared__ MarchSmem<kBX>          sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MarchSmem<kBX> &                  sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
   MarchThread<kBX, SOLVER, FUSE_DT> th;
   if (!th.init(a, sm, threadIdx.x, blockIdx.x, blockIdx.y))
     return;
@@ -623,6 +624,96 @@ k_eval(Settings s, int func, const double * __restrict__ in, double * __restrict
       double *       o = out + 8 * r;
       riemann_approx(s, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP],
                      o[IU], o[IV], o[4 + ID], o[4 + IP], o[4 + IU], o[4 + IV]);
+      break;
+    }
+    case 7:
+    { // hllc_lean: the fused kernel's solver, fast path then (guard failed) plain operators; out[4] = guard
+      const double *   a = in + 8 * r;
+      double *         o = out + 5 * r;
+      const StepConsts c = make_step_consts(s);
+      bool             ok = true;
+      hllc_lean<true>(s, c, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP], o[IU],
+                      o[IV], ok);
+      o[4] = ok ? 1.0 : 0.0;
+      if (!ok)
+        hllc_lean<false>(s, c, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP],
+                         o[IU], o[IV], ok);
+      break;
+    }
+    case 8:
+    { // prim_lean + cfl_lean: q[4], invDt integrand, guard
+      const double *   a = in + 4 * r;
+      double *         o = out + 6 * r;
+      const StepConsts c = make_step_consts(s);
+      bool             ok = true, unused = true;
+      Recip            rd;
+      const Recip      rdx = recip_of<true, false>(s.dx, unused), rdy = recip_of<true, false>(s.dy, unused);
+      prim_lean<true>(s, c, a, o, rd, ok);
+      o[4] = cfl_lean<true>(s, c, rdx, rdy, a, ok);
+      o[5] = ok ? 1.0 : 0.0;
+      if (!ok)
+      {
+        prim_lean<false>(s, c, a, o, rd, ok);
+        o[4] = cfl_lean<false>(s, c, rdx, rdy, a, ok);
+      }
+      break;
+    }
+    case 9:
+    { // slope_lean + trace_sources_lean + faces: same record as "trace" but slopes are recomputed from the
+      // 5-point stencil: in = q, qPlusX, qMinusX, qPlusY, qMinusY, dtdx, dtdy (22); out = dqX, dqY, 4 faces, guard (25)
+      const double * a = in + 22 * r;
+      double *       o = out + 25 * r;
+      const bool     limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
+      double         dqX[4], dqY[4], s0[4], f[4];
+      slopes_lean(s.slope_type, limited, a, a + 4, a + 8, dqX);
+      slopes_lean(s.slope_type, limited, a, a + 12, a + 16, dqY);
+      bool  ok = true, unused = true;
+      Recip rd = recip_of<true, true>(a[ID], unused);
+      trace_sources_lean<true>(s, a, rd, dqX, dqY, s0, ok);
+      o[24] = ok ? 1.0 : 0.0;
+      if (!ok)
+        trace_sources_lean<false>(s, a, rd, dqX, dqY, s0, ok);
+      for (int v = 0; v < 4; ++v)
+      {
+        o[v] = dqX[v];
+        o[4 + v] = dqY[v];
+      }
+      trace_face<-1>(s, a, dqX, s0, a[20], f);
+      for (int v = 0; v < 4; ++v)
+        o[8 + v] = f[v];
+      trace_face<+1>(s, a, dqX, s0, a[20], f);
+      for (int v = 0; v < 4; ++v)
+        o[12 + v] = f[v];
+      trace_face<-1>(s, a, dqY, s0, a[21], f);
+      for (int v = 0; v < 4; ++v)
+        o[16 + v] = f[v];
+      trace_face<+1>(s, a, dqY, s0, a[21], f);
+      for (int v = 0; v < 4; ++v)
+        o[20 + v] = f[v];
+      break;
+    }
+    case 10:
+    { // div: a, d -> shared-reciprocal quotient (ZERO_OK), its guard, the `/` operator, same with ZERO_OK off
+      const double * a = in + 2 * r;
+      double *       o = out + 5 * r;
+      bool           ok = true, ok2 = true;
+      const Recip    rp = recip_of<true, true>(a[1], ok);
+      o[0] = div_by<true, true>(a[0], rp, ok);
+      o[1] = ok ? 1.0 : 0.0;
+      o[2] = a[0] / a[1];
+      const Recip rn = recip_of<true, false>(a[1], ok2);
+      o[3] = div_by<true, false>(a[0], rn, ok2);
+      o[4] = ok2 ? 1.0 : 0.0;
+      break;
+    }
+    case 11:
+    { // sqrt: x -> lean sqrt, guard, sqrt()
+      const double * a = in + r;
+      double *       o = out + 3 * r;
+      bool           ok = true;
+      o[0] = sqrt_pos<true>(a[0], ok);
+      o[1] = ok ? 1.0 : 0.0;
+      o[2] = sqrt(a[0]);
       break;
     }
     case 5:
@@ -908,13 +999,28 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
   const int  sol = solver_for(p);
   const bool fuse = d_invdt_bits != nullptr;
-#define E2D_FS(SOL)                                              \
-  do                                                             \
-  {                                                              \
-    if (fuse)                                                    \
-      k_fused_step<SOL, true><<<grid, kBX, 0, st>>>(a, d_done);  \
-    else                                                         \
-      k_fused_step<SOL, false><<<grid, kBX, 0, st>>>(a, d_done); \
+  const size_t smem = sizeof(MarchSmem<kBX>);
+#define E2D_FS1(SOL, FUSE)                                                                                        \
+  do                                                                                                              \
+  {                                                                                                               \
+    static bool configured = false; /* per instantiation; benign race: the attribute is idempotent */            \
+    if (!configured)                                                                                              \
+    {                                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           (int)smem);                                                            \
+      if (e != cudaSuccess)                                                                                       \
+        return e;                                                                                                 \
+      configured = true;                                                                                          \
+    }                                                                                                             \
+    k_fused_step<SOL, FUSE><<<grid, kBX, smem, st>>>(a, d_done);                                                  \
+  } while (0)
+#define E2D_FS(SOL)       \
+  do                      \
+  {                       \
+    if (fuse)             \
+      E2D_FS1(SOL, true); \
+    else                  \
+      E2D_FS1(SOL, false);\
   } while (0)
   if (sol == 0)
     E2D_FS(0);
@@ -923,6 +1029,7 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   else
     E2D_FS(2);
 #undef E2D_FS
+#undef E2D_FS1
   count_launch();
   return cudaGetLastError();
 }

@@ -23,7 +23,8 @@
 // Shared memory (ring slots are row % 3 or row & 1; one barrier per row suffices):
 //   Q[r%3]       primitives of rows r-1, r, r+1      written in B(r-2)   read in A(r-1..r+1)
 //   RY[r%3]      refined 1/rho of the same rows      own column only
-//   U[r&1]       conservatives of rows r, r+1        own column only     written B(r-2), read B(r)
+//   U[r%3]       conservatives of rows r, r+1, r+2   own column only     row r+2 lands by cp.async issued in
+//                                                                        A(r), is read in B(r) (-> Q) and B(r+2)
 //   XMAX[r&1]    XMAX face states of row r           written in A(r)     read in B(r) by the east lane
 //   YMAX[r&1]    YMAX face states of row r           own column only     written A(r), read B(r+1)
 //   FX[(r+1)&1]  x fluxes of row r                   written in B(r)     read in B(r+1) by the west lane
@@ -63,7 +64,7 @@ struct MarchSmem
 {
   double Q[3][4][BX];
   double RY[3][BX];
-  double U[2][4][BX];
+  double U[3][4][BX];
   double XMAX[2][4][BX];
   double YMAX[2][4][BX];
   double FX[2][4][BX];
@@ -100,6 +101,34 @@ struct MarchThread
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
       u[v] = p[v * plane];
+  }
+
+  // asynchronous fetch of this thread's cell of row j into U ring slot `slot` (cp.async: no registers are
+  // held while the load is in flight, so the compiler cannot sink it towards its consumer)
+  E2D_HD void
+  prefetch_row(const MarchArgs & a, MarchSmem<BX> & sm, int j, int slot) const
+  {
+    const double * p = a.Uin + (size_t)j * a.isize + ic;
+#if E2D_LEAN_DEVICE
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+    {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.U[slot][v][t]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p + v * plane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+    for (int v = 0; v < 4; ++v)
+      sm.U[slot][v][t] = p[v * plane];
+#endif
+  }
+
+  E2D_HD void
+  wait_prefetch() const
+  {
+#if E2D_LEAN_DEVICE
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
   }
 
   // conservative -> primitive of one cell of a fetched row, into ring slot `slot`
@@ -168,13 +197,13 @@ struct MarchThread
     convert_into(a, sm, u, (j0 - 1) % 3);
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
-      sm.U[(j0 - 1) & 1][v][t] = u[v];
+      sm.U[(j0 - 1) % 3][v][t] = u[v];
     load_row(a, j0, u);
     convert_into(a, sm, u, j0 % 3);
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      sm.U[j0 & 1][v][t] = u[v];
+      sm.U[j0 % 3][v][t] = u[v];
       sm.YMAX[(j0 - 2) & 1][v][t] = u[v]; // any valid state: the south face of row j0-1 is solved but unused
       sm.FX[(j0 - 1) & 1][v][t] = 0.0;    // read (and unused) by the first phase B
       fyP[v] = 0.0;
@@ -190,6 +219,9 @@ struct MarchThread
     const Settings & s = a.s;
     const int        sC = m3, sS = (m3 == 0) ? 2 : m3 - 1, sN = (m3 == 2) ? 0 : m3 + 1;
     double           qC[4], qW[4], qE[4], qS[4], qN[4], dqX[4], dqY[4], s0[4], xmax[4], ymax[4];
+    // row r+2 (clamped: the last fetch of the topmost segment is a harmless repeat) -> U ring slot of row r-1,
+    // consumed at the bottom of phase B
+    prefetch_row(a, sm, (r + 2 < a.jsize) ? r + 2 : a.jsize - 1, sS);
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
@@ -258,13 +290,6 @@ struct MarchThread
   E2D_HD void
   phaseB(const MarchArgs & a, MarchSmem<BX> & sm, int r)
   {
-    // fetch row r+2 (clamped: the last fetch of the topmost segment is a harmless repeat), consumed at the bottom
-    double uP[4];
-    {
-      const int jn = (r + 2 < a.jsize) ? r + 2 : a.jsize - 1;
-      load_row(a, jn, uP);
-    }
-
     double xl[4], yl[4], fxE[4], uC[4], fx[4], fy[4], un[4], cflv;
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -272,7 +297,7 @@ struct MarchThread
       xl[v] = sm.XMAX[r & 1][v][tm];
       yl[v] = sm.YMAX[(r - 1) & 1][v][t];
       fxE[v] = sm.FX[r & 1][v][tp];
-      uC[v] = sm.U[r & 1][v][t];
+      uC[v] = sm.U[m3][v][t];
     }
     bool ok = true;
     compute_B<true>(a, xl, yl, fxE, fx, fy, un, cflv, ok);
@@ -300,12 +325,14 @@ struct MarchThread
       fyP[v] = fy[v];
     }
 
-    // row r+2 -> rings (slot of row r-1 in Q/RY, slot of row r in U: both consumed above / in A(r))
+    // row r+2 (fetched since phase A) -> primitive ring, slot of row r-1 (last read in A(r))
     const int sS = (m3 == 0) ? 2 : m3 - 1;
-    convert_into(a, sm, uP, sS);
+    double    uP[4];
+    wait_prefetch();
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
-      sm.U[r & 1][v][t] = uP[v];
+      uP[v] = sm.U[sS][v][t];
+    convert_into(a, sm, uP, sS);
     m3 = (m3 == 2) ? 0 : m3 + 1;
   }
 };

@@ -159,6 +159,14 @@ int e2d_k_fused_step(const e2d_params * p, const double * Uin, double * Uout, in
  *   "approx" qleft, qright (8)                                qgdnv[4], flux[4]    riemann_approx :558-693
  *   "cmpflx" qgdnv (4)                                        flux[4]              cmpflx :523-547
  *   "hll"    qleft, qright (8)                                flux[4]              (extension: not in the reference)
+ * and the lean-but-exact forms the fused kernel uses (csrc/e2d_lean.cuh), each with its fast-path guard (1 = the
+ * fast path was accepted, 0 = the value comes from the plain-operator fallback):
+ *   "hllc_lean"   qleft, qright (8)                           flux[4], guard
+ *   "cell_lean"   u[4]                                        q[4], CFL integrand (c+|u|)/dx+(c+|v|)/dy, guard
+ *   "trace_lean"  q, qPlusX, qMinusX, qPlusY, qMinusY, dtdx, dtdy (22)   dqX, dqY, XMIN, XMAX, YMIN, YMAX (24), guard
+ *   "div"         a, d                                        shared-reciprocal a/d (zero numerators allowed), guard,
+ *                                                             a/d by the `/` operator, same without zeros, guard
+ *   "sqrt"        x                                           fast-path sqrt, guard, sqrt(x)
  */
 int e2d_k_eval_host(const e2d_params * p, const char * func, const double * in, double * out, long n);
 

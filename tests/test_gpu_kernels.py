@@ -108,6 +108,114 @@ def test_hll_extension_is_consistent():
     np.testing.assert_allclose(gpu_eval(hp, "hll", rec), gpu_eval(hp, "hllc", rec), rtol=1e-13)
 
 
+# ------------------------------------------------------------------ the fused kernel's lean-but-exact math
+def adversarial_doubles(rng, n):
+    """Doubles spread over the whole exponent range, both signs, with zeros, subnormals and hard mantissas."""
+    mant = rng.uniform(1.0, 2.0, n)
+    mant[::11] = np.nextafter(2.0, 0.0)   # all-ones mantissa
+    mant[1::11] = 1.0
+    mant[2::11] = np.nextafter(1.0, 2.0)
+    expo = rng.integers(-1070, 1023, n)
+    x = np.ldexp(mant, expo) * rng.choice([-1.0, 1.0], n)
+    x[3::17] = 0.0
+    x[4::17] = -0.0
+    return x
+
+
+def test_shared_reciprocal_division_is_correctly_rounded():
+    """div_by (csrc/e2d_lean.cuh): wherever its guard accepts the fast path the quotient is bit-identical to
+    the IEEE `/` (and to numpy's), over the whole exponent range, signed zeros included."""
+    hp, _ = kat_params("1.4")
+    rng = np.random.default_rng(99)
+    n = 1 << 18
+    a, d = adversarial_doubles(rng, n), adversarial_doubles(rng, n)
+    # a moderate-range block like the solver sees (most of these must stay on the fast path)
+    a[: n // 2] = rng.normal(0, 3, n // 2) * 10.0 ** rng.integers(-12, 6, n // 2)
+    d[: n // 2] = np.abs(rng.normal(0, 3, n // 2)) * 10.0 ** rng.integers(-9, 6, n // 2) + 1e-300
+    a[5 : n // 2 : 13] = 0.0
+    a[6 : n // 2 : 13] = -0.0
+    out = gpu_eval(hp, "div", np.stack([a, d], axis=1))
+    with np.errstate(all="ignore"):
+        ref = a / d
+    assert_bitwise(out[:, 2], ref, "device `/` vs numpy")  # sanity of the comparison itself
+    for col, gcol, what in ((0, 1, "zero-ok"), (3, 4, "plain")):
+        ok = out[:, gcol] == 1.0
+        assert_bitwise(out[ok, col], ref[ok], f"shared-reciprocal quotient ({what})")
+    okz, okp = out[:, 1] == 1.0, out[:, 4] == 1.0
+    assert okz[: n // 2].mean() > 0.99, "moderate-range quotients must stay on the fast path"
+    zero_num = (a == 0) & (d >= 2.3e-308) & np.isfinite(d)
+    assert okz[zero_num].all(), "zero numerators over positive denominators stay on the fast path"
+    assert not okp[(a == 0) & np.isfinite(d) & (d != 0)].any(), "without ZERO_OK a zero numerator must be rejected"
+    assert not okz[(d <= 0)].any(), "ZERO_OK requires a positive denominator"
+
+
+def test_fast_path_sqrt_is_correctly_rounded():
+    hp, _ = kat_params("1.4")
+    rng = np.random.default_rng(5)
+    n = 1 << 18
+    x = np.abs(adversarial_doubles(rng, n))
+    x[: n // 2] = rng.uniform(0, 4, n // 2) * 10.0 ** rng.integers(-20, 20, n // 2)
+    # squares of random doubles +- 1ulp: results next to rounding boundaries
+    r = rng.uniform(1, 2, n // 4)
+    x[n // 2 : n // 2 + n // 4] = np.nextafter(r * r, rng.choice([0.0, 10.0], n // 4))
+    out = gpu_eval(hp, "sqrt", x[:, None])
+    ref = np.sqrt(x)
+    assert_bitwise(out[:, 2], ref, "device sqrt() vs numpy")
+    ok = out[:, 1] == 1.0
+    assert_bitwise(out[ok, 0], ref[ok], "fast-path sqrt")
+    assert ok[: n // 2][x[: n // 2] > 1e-250].all()
+
+
+@pytest.mark.parametrize("gamma", ["1.4", "1.666"])
+def test_lean_device_functions_match_oracle(gamma):
+    """hllc_lean / prim_lean / cfl_lean / slope_lean / trace_sources_lean == the reference formulas, bit for bit,
+    including states at rest (zero numerators), identical states and supersonic states."""
+    hp, op = kat_params(gamma)
+    rng = np.random.default_rng(4321)
+    n = 8192
+    rec = np.concatenate([random_state(rng, n), random_state(rng, n)], axis=1)
+    rec[::7, 2] += 8.0
+    rec[::7, 6] += 8.0
+    rec[1::7, 2] -= 8.0
+    rec[1::7, 6] -= 8.0
+    rec[2::7, 4:8] = rec[2::7, 0:4]      # identical states
+    rec[3::7, 2:4] = 0.0                 # gas at rest on both sides, equal pressure: ustar numerator is exactly 0
+    rec[3::7, 6:8] = 0.0
+    rec[3::7, 5] = rec[3::7, 1]
+    rec[4::7, 2] = -0.0                  # signed zero normal velocity
+    rec[5::70, 0] = 1e-300               # absurd states: must fall back, still exact
+    rec[6::70, 1] = 1e-280
+    out = gpu_eval(hp, "hllc_lean", rec)
+    assert_bitwise(out[:, :4], oracle.riemann_hllc(op, rec), f"hllc_lean gamma={gamma}")
+    assert (out[:, 4] == 1.0).mean() > 0.95, "ordinary states must stay on the fast path"
+
+    q = random_state(rng, n)
+    u = np.stack([q[:, 0], q[:, 1] / 0.4 + 0.5 * q[:, 0] * (q[:, 2] ** 2 + q[:, 3] ** 2), q[:, 0] * q[:, 2],
+                  q[:, 0] * q[:, 3]], axis=1)
+    u[::5, 2] = 0.0
+    u[1::5, 3] = -0.0
+    u[::97, 0] = 1e-12
+    u[7::500, 2] = 1e-300
+    out = gpu_eval(hp, "cell_lean", u)
+    qo, co = oracle.compute_primitives(op, u)
+    assert_bitwise(out[:, :4], qo, f"prim_lean gamma={gamma}")
+    inv = (co + np.abs(qo[:, 2])) / op.dx + (co + np.abs(qo[:, 3])) / op.dy
+    assert_bitwise(out[:, 4], inv, f"cfl_lean gamma={gamma}")
+    assert (out[:, 5] == 1.0).mean() > 0.99
+
+    st = np.concatenate([random_state(rng, n) for _ in range(5)], axis=1)
+    st[::5, 4:8] = st[::5, 0:4]          # flat on one side -> zero slopes -> zero numerators in the trace
+    st[1::5, 4:20] = np.tile(st[1::5, 0:4], 4)   # completely flat
+    st[2::50, 2] = -0.0
+    dts = rng.uniform(0.05, 0.5, (n, 2))
+    out = gpu_eval(hp, "trace_lean", np.concatenate([st, dts], axis=1))
+    dq = oracle.slopes(op, st)
+    assert_bitwise(out[:, :8], dq, f"slope_lean gamma={gamma}")
+    ref = oracle.trace(op, np.concatenate([st[:, :4], dq, dts], axis=1))
+    assert_bitwise(out[:, 8:24], ref, f"trace_lean gamma={gamma}")
+    assert (out[:, 24] == 1.0).mean() > 0.99
+
+
 # ------------------------------------------------------------------ boundary fill: bit-exact
 BC_CASES = [(1, 1, 1, 1), (2, 2, 2, 2), (3, 3, 3, 3), (3, 3, 2, 1), (1, 2, 3, 3), (2, 1, 1, 2)]
 
