@@ -254,6 +254,9 @@ check_slab_args(const e2d_params * p, int jsize_loc)
   // an earlier pass (src/HydroRunFunctors.h:1895,1933), which the single-launch fill does not reproduce
   if (p->nx < 2 || p->isize != p->nx + 4 || jsize_loc < 6 || p->ghostWidth != 2)
     return fail(E2D_ERR_INVALID, "inconsistent geometry (need nx>=2, isize=nx+4, jsize_loc>=6, ghostWidth=2)");
+  // the kernels index one variable plane with 32-bit offsets (the reference does too: `int ijsize`, HydroRun.h:511)
+  if ((long long)p->isize * (long long)jsize_loc >= (1ll << 31))
+    return fail(E2D_ERR_UNSUPPORTED, "slab too large: isize*jsize_loc must stay below 2^31 cells per device");
   return E2D_OK;
 }
 

@@ -4,6 +4,7 @@
 // reference's FMA-free x86 build).  Data layout: SoA planes, off = i + isize*(j + jsize*var);
 // threadIdx.x always walks i, so every global access of a warp is a contiguous 256-byte run.
 #include <cstdio>
+#include <cstdlib>
 
 #include "e2d_internal.h"
 #include "e2d_march.cuh" // includes e2d_lean.cuh
@@ -15,7 +16,7 @@ namespace
 {
 
 constexpr int kBX = 128;       // threads per block of the marching kernel (= columns incl. 4 halo columns)
-constexpr int kMarchMinBlocks = 4;
+constexpr int kMarchMinBlocks = 3; // blocks of 128 threads per SM (<= 168 registers per thread)
 
 __host__ __device__ __forceinline__ size_t
 cell(const Geom & g, int i, int j, int v)
@@ -521,6 +522,7 @@ k_fused_step(MarchArgs a, const int * __restrict__ d_done)
     __syncthreads();
     th.phaseB(a, sm, r);
   }
+  th.finish(a);
   if (FUSE_DT && a.invdt_bits)
     block_max_to_global(th.invdt, a.invdt_bits);
 }
@@ -678,16 +680,16 @@ k_eval(Settings s, int func, const double * __restrict__ in, double * __restrict
         o[v] = dqX[v];
         o[4 + v] = dqY[v];
       }
-      trace_face<-1>(s, a, dqX, s0, a[20], f);
+      trace_face_lean<-1>(s, a, dqX, s0, a[20], f);
       for (int v = 0; v < 4; ++v)
         o[8 + v] = f[v];
-      trace_face<+1>(s, a, dqX, s0, a[20], f);
+      trace_face_lean<+1>(s, a, dqX, s0, a[20], f);
       for (int v = 0; v < 4; ++v)
         o[12 + v] = f[v];
-      trace_face<-1>(s, a, dqY, s0, a[21], f);
+      trace_face_lean<-1>(s, a, dqY, s0, a[21], f);
       for (int v = 0; v < 4; ++v)
         o[16 + v] = f[v];
-      trace_face<+1>(s, a, dqY, s0, a[21], f);
+      trace_face_lean<+1>(s, a, dqY, s0, a[21], f);
       for (int v = 0; v < 4; ++v)
         o[20 + v] = f[v];
       break;
@@ -951,32 +953,34 @@ launch_update_dir(const e2d_params &, const Geom & g, double * U, const double *
   return cudaGetLastError();
 }
 
-// rows per block segment: as long as possible (2 warm-up rows per segment are redundant work) while
-// still cutting the grid into enough blocks to keep 148 SMs x 3 resident blocks busy for several waves
+// Rows per block segment.  Every segment re-traces 2 rows and re-converts 3, so segments should be long; but
+// the grid (nbx column blocks x nseg segments) should also fill the 148 SMs x blocks_per_sm resident slots in
+// an integral number of equal waves, because a block lives for a whole segment.  Pick the segment count that
+// minimises  waves x (rows per segment + per-segment overhead).
 static int
-choose_seg_rows(int nbx, int ny)
+choose_seg_rows(int nbx, int ny, int blocks_per_sm)
 {
-  const int slots = 148 * kMarchMinBlocks;
-  int       best = ny;
-  for (int waves = 8; waves >= 1; --waves)
+  const int  slots = 148 * blocks_per_sm;
+  const int  overhead_rows = 4;
+  long       best_cost = -1;
+  int        best_rows = ny;
+  const int  max_seg = ny < 4096 ? ny : 4096;
+  for (int nseg = 1; nseg <= max_seg; ++nseg)
   {
-    const int want_blocks = slots * waves;
-    int       nseg = (want_blocks + nbx - 1) / nbx;
-    if (nseg < 1)
-      nseg = 1;
-    int rows = (ny + nseg - 1) / nseg;
-    if (rows >= 32)
+    const int  rows = (ny + nseg - 1) / nseg;
+    const int  used = (ny + rows - 1) / rows; // segments actually needed with this row count
+    const long blocks = (long)nbx * used;
+    const long waves = (blocks + slots - 1) / slots;
+    const long cost = waves * (rows + overhead_rows);
+    if (best_cost < 0 || cost < best_cost)
     {
-      best = rows;
-      break;
+      best_cost = cost;
+      best_rows = rows;
     }
-    best = rows < 8 ? 8 : rows;
+    if (rows <= 8)
+      break;
   }
-  if (best > ny)
-    best = ny;
-  if (best < 1)
-    best = 1;
-  return best;
+  return best_rows < 1 ? 1 : best_rows;
 }
 
 cudaError_t
@@ -994,33 +998,33 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   a.d_dt = d_dt;
   a.invdt_bits = d_invdt_bits;
   const int nbx = (g.nx + (kBX - 4) - 1) / (kBX - 4);
-  a.seg_rows = choose_seg_rows(nbx, g.ny);
+  a.seg_rows = choose_seg_rows(nbx, g.ny, kMarchMinBlocks);
   const int  nseg = (g.ny + a.seg_rows - 1) / a.seg_rows;
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
   const int  sol = solver_for(p);
   const bool fuse = d_invdt_bits != nullptr;
   const size_t smem = sizeof(MarchSmem<kBX>);
-#define E2D_FS1(SOL, FUSE)                                                                                        \
-  do                                                                                                              \
-  {                                                                                                               \
-    static bool configured = false; /* per instantiation; benign race: the attribute is idempotent */            \
-    if (!configured)                                                                                              \
-    {                                                                                                             \
-      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                           (int)smem);                                                            \
-      if (e != cudaSuccess)                                                                                       \
-        return e;                                                                                                 \
-      configured = true;                                                                                          \
-    }                                                                                                             \
-    k_fused_step<SOL, FUSE><<<grid, kBX, smem, st>>>(a, d_done);                                                  \
+#define E2D_FS1(SOL, FUSE)                                                                                       \
+  do                                                                                                             \
+  {                                                                                                              \
+    static bool configured = false; /* per instantiation; benign race: setting the attribute is idempotent */   \
+    if (!configured)                                                                                             \
+    {                                                                                                            \
+      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem);                                                           \
+      if (e != cudaSuccess)                                                                                      \
+        return e;                                                                                                \
+      configured = true;                                                                                         \
+    }                                                                                                            \
+    k_fused_step<SOL, FUSE><<<grid, kBX, smem, st>>>(a, d_done);                                                 \
   } while (0)
-#define E2D_FS(SOL)       \
-  do                      \
-  {                       \
-    if (fuse)             \
-      E2D_FS1(SOL, true); \
-    else                  \
-      E2D_FS1(SOL, false);\
+#define E2D_FS(SOL)        \
+  do                       \
+  {                        \
+    if (fuse)              \
+      E2D_FS1(SOL, true);  \
+    else                   \
+      E2D_FS1(SOL, false); \
   } while (0)
   if (sol == 0)
     E2D_FS(0);

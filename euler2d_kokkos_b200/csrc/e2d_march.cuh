@@ -28,8 +28,9 @@
 //   XMAX[r&1]    XMAX face states of row r           written in A(r)     read in B(r) by the east lane
 //   YMAX[r&1]    YMAX face states of row r           own column only     written A(r), read B(r+1)
 //   FX[(r+1)&1]  x fluxes of row r                   written in B(r)     read in B(r+1) by the west lane
-// Keeping the own-column rows in shared memory instead of registers is what brings the kernel under
-// 128 registers (4 blocks of 128 threads per SM instead of 3).
+// Own-column rows live in shared memory rather than registers: cp.async needs a shared-memory target anyway,
+// and it keeps the register file for the solver's temporaries (ncu: 3 blocks/SM at <=168 registers beat 4
+// blocks/SM at 128, profiles/r1_fused_step_variants.txt).
 //
 // All work is unconditional (rows outside [j0, j1) compute on valid-but-unused data); only the side
 // effects are predicated.  The arithmetic is the lean-but-exact form of e2d_lean.cuh; when a fast-path
@@ -92,12 +93,14 @@ struct MarchThread
   double xmin[4], ymin[4]; // XMIN / YMIN face states of row r (A -> B)
   double fyP[4];           // y flux at the south face of row r-1
   double pend[4];          // U(r-1) + Fx(i, r-1)
+  double unD[4];           // updated state of the row completed by the previous phase B (CFL integrand deferred)
   double invdt;
 
   E2D_HD void
   load_row(const MarchArgs & a, int j, double u[4]) const
   {
-    const double * p = a.Uin + (size_t)j * a.isize + ic;
+    // 32-bit in-plane offset (isize*jsize < 2^31 is checked at the ABI); the plane stride is block-uniform
+    const double * p = a.Uin + (j * a.isize + ic);
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
       u[v] = p[v * plane];
@@ -108,7 +111,7 @@ struct MarchThread
   E2D_HD void
   prefetch_row(const MarchArgs & a, MarchSmem<BX> & sm, int j, int slot) const
   {
-    const double * p = a.Uin + (size_t)j * a.isize + ic;
+    const double * p = a.Uin + (j * a.isize + ic);
 #if E2D_LEAN_DEVICE
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -148,19 +151,6 @@ struct MarchThread
     for (int v = 0; v < 4; ++v)
       sm.Q[slot][v][t] = q[v];
     sm.RY[slot][t] = rd.y;
-  }
-
-  template <bool LEAN>
-  E2D_HD void
-  solve(const MarchArgs & a, const double l[4], const double r[4], int in, int it, double f[4], bool & ok) const
-  {
-    // in / it: index of the normal / transverse velocity (IU, IV for x faces; swapped for y faces,
-    // src/HydroRunFunctors.h:628-632)
-    if (SOLVER == 2)
-      hllc_lean<LEAN>(a.s, a.c, l[ID], l[IP], l[in], l[it], r[ID], r[IP], r[in], r[it], f[ID], f[IP], f[in], f[it],
-                      ok);
-    else
-      riemann<SOLVER>(a.s, l[ID], l[IP], l[in], l[it], r[ID], r[IP], r[in], r[it], f[ID], f[IP], f[in], f[it]);
   }
 
   // returns false when the block has no rows to produce (uniform over the block)
@@ -208,6 +198,7 @@ struct MarchThread
       sm.FX[(j0 - 1) & 1][v][t] = 0.0;    // read (and unused) by the first phase B
       fyP[v] = 0.0;
       pend[v] = 0.0;
+      unD[v] = u[v]; // any valid state
     }
     return true;
   }
@@ -244,10 +235,10 @@ struct MarchThread
     trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
     if (!ok)
       trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
-    trace_face<-1>(s, qC, dqX, s0, dtdx, xmin);
-    trace_face<+1>(s, qC, dqX, s0, dtdx, xmax);
-    trace_face<-1>(s, qC, dqY, s0, dtdy, ymin);
-    trace_face<+1>(s, qC, dqY, s0, dtdy, ymax);
+    trace_face_lean<-1>(s, qC, dqX, s0, dtdx, xmin);
+    trace_face_lean<+1>(s, qC, dqX, s0, dtdx, xmax);
+    trace_face_lean<-1>(s, qC, dqY, s0, dtdy, ymin);
+    trace_face_lean<+1>(s, qC, dqY, s0, dtdy, ymax);
 
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -257,15 +248,32 @@ struct MarchThread
     }
   }
 
-  // everything of phase B that is arithmetic: the two face solves, the update of row r-1 and its CFL integrand
+  // Everything of phase B that is arithmetic: the x-face and y-face solves, the update of row r-1, and — advanced
+  // in lock step (e2d_lean.cuh) — the primitives of the fetched row r+2 together with the primitives + CFL
+  // integrand of the row completed by the PREVIOUS phase B (deferred by one row so that its long serial chain
+  // overlaps other work instead of trailing the update).
   template <bool LEAN>
   E2D_HD void
-  compute_B(const MarchArgs & a, const double xl[4], const double yl[4], const double fxE[4], double fx[4], double fy[4], double un[4], double & cflv, bool & ok) const
+  compute_B(const MarchArgs & a, const double xl[4], const double yl[4], const double fxE[4], const double uP[4],
+            double fx[4], double fy[4], double un[4], double qP[4], double & ryP, double & cflv, bool & ok) const
   {
-    // west face of cell (i, r): left = XMAX of (i-1, r), right = XMIN of (i, r) (HydroRunFunctors.h:559-575)
-    solve<LEAN>(a, xl, xmin, IU, IV, fx, ok);
-    // south face of row r: left = YMAX of row r-1, right = YMIN of row r, IU<->IV swapped (:621-640)
-    solve<LEAN>(a, yl, ymin, IV, IU, fy, ok);
+    const Settings & s = a.s;
+    if (SOLVER == 2)
+    {
+      // west face of cell (i, r): left = XMAX of (i-1, r), right = XMIN of (i, r) (HydroRunFunctors.h:559-575)
+      hllc_lean<LEAN>(s, a.c, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP],
+                      fx[IU], fx[IV], ok);
+      // south face of row r: left = YMAX of row r-1, right = YMIN of row r, IU<->IV swapped (:621-640)
+      hllc_lean<LEAN>(s, a.c, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP],
+                      fy[IV], fy[IU], ok);
+    }
+    else
+    {
+      riemann<SOLVER>(s, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP], fx[IU],
+                      fx[IV]);
+      riemann<SOLVER>(s, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP], fy[IV],
+                      fy[IU]);
+    }
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
@@ -284,13 +292,45 @@ struct MarchThread
     }
     cflv = 0.0;
     if (FUSE_DT)
-      cflv = cfl_lean<LEAN>(a.s, a.c, rdx, rdy, un, ok);
+    {
+      double u2[2][4], q2[2][4];
+      Recip  rd2[2];
+      E2D_UNROLL
+      for (int v = 0; v < 4; ++v)
+      {
+        u2[0][v] = unD[v];
+        u2[1][v] = uP[v];
+      }
+      prim_lean_multi<LEAN, 2>(s, a.c, u2, q2, rd2, ok);
+      cflv = cfl_tail_lean<LEAN>(s, rdx, rdy, q2[0], rd2[0], ok);
+      E2D_UNROLL
+      for (int v = 0; v < 4; ++v)
+        qP[v] = q2[1][v];
+      if (LEAN)
+        ryP = rd2[1].y;
+    }
+    else
+    {
+      double u1[1][4], q1[1][4];
+      Recip  rd1[1];
+      E2D_UNROLL
+      for (int v = 0; v < 4; ++v)
+        u1[0][v] = uP[v];
+      prim_lean_multi<LEAN, 1>(s, a.c, u1, q1, rd1, ok);
+      E2D_UNROLL
+      for (int v = 0; v < 4; ++v)
+        qP[v] = q1[0][v];
+      if (LEAN)
+        ryP = rd1[0].y;
+    }
   }
 
   E2D_HD void
   phaseB(const MarchArgs & a, MarchSmem<BX> & sm, int r)
   {
-    double xl[4], yl[4], fxE[4], uC[4], fx[4], fy[4], un[4], cflv;
+    const int sS = (m3 == 0) ? 2 : m3 - 1;
+    double    xl[4], yl[4], fxE[4], uC[4], uP[4], fx[4], fy[4], un[4], qP[4], ryP = 0.0, cflv;
+    wait_prefetch(); // row r+2, in flight since phase A
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
@@ -298,24 +338,30 @@ struct MarchThread
       yl[v] = sm.YMAX[(r - 1) & 1][v][t];
       fxE[v] = sm.FX[r & 1][v][tp];
       uC[v] = sm.U[m3][v][t];
+      uP[v] = sm.U[sS][v][t];
     }
     bool ok = true;
-    compute_B<true>(a, xl, yl, fxE, fx, fy, un, cflv, ok);
+    compute_B<true>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
     if (!ok)
-      compute_B<false>(a, xl, yl, fxE, fx, fy, un, cflv, ok);
+      compute_B<false>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
 
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
+    {
       sm.FX[(r + 1) & 1][v][t] = fx[v];
+      sm.Q[sS][v][t] = qP[v]; // row r+2 -> primitive ring, slot of row r-1 (last read in A(r))
+    }
+    sm.RY[sS][t] = ryP;
 
+    // the CFL integrand just computed belongs to row r-2 (completed by the previous phase B)
+    if (FUSE_DT && store && r >= j0 + 2)
+      invdt = fmax(invdt, cflv); // fmax drops a NaN operand like the reference's reduction (:72)
     if (store && r >= j0 + 1)
     {
-      double * po = a.Uout + (size_t)(r - 1) * a.isize + i;
+      double * po = a.Uout + ((r - 1) * a.isize + i);
       E2D_UNROLL
       for (int v = 0; v < 4; ++v)
         po[v * plane] = un[v];
-      if (FUSE_DT)
-        invdt = fmax(invdt, cflv); // fmax drops a NaN operand like the reference's reduction (:72)
     }
 
     E2D_UNROLL
@@ -323,17 +369,29 @@ struct MarchThread
     {
       pend[v] = uC[v] + fx[v];
       fyP[v] = fy[v];
+      unD[v] = un[v];
     }
-
-    // row r+2 (fetched since phase A) -> primitive ring, slot of row r-1 (last read in A(r))
-    const int sS = (m3 == 0) ? 2 : m3 - 1;
-    double    uP[4];
-    wait_prefetch();
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-      uP[v] = sm.U[sS][v][t];
-    convert_into(a, sm, uP, sS);
     m3 = (m3 == 2) ? 0 : m3 + 1;
+  }
+
+  // after the last phase B: the CFL integrand of the last completed row (j1-1)
+  E2D_HD void
+  finish(const MarchArgs & a)
+  {
+    if (!FUSE_DT)
+      return;
+    bool   ok = true;
+    double q[4];
+    Recip  rd;
+    prim_lean<true>(a.s, a.c, unD, q, rd, ok);
+    double v = cfl_tail_lean<true>(a.s, rdx, rdy, q, rd, ok);
+    if (!ok)
+    {
+      prim_lean<false>(a.s, a.c, unD, q, rd, ok);
+      v = cfl_tail_lean<false>(a.s, rdx, rdy, q, rd, ok);
+    }
+    if (store)
+      invdt = fmax(invdt, v);
   }
 };
 

@@ -70,7 +70,10 @@ run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_lo
           th[t].phaseB(a, *sm, r);
       }
       for (int t = 0; t < BX; ++t)
+      {
+        th[t].finish(a);
         invdt = std::fmax(invdt, th[t].invdt);
+      }
     }
   delete sm;
   return invdt;
