@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 NX_PER_GPU = 8192
 NY_PER_GPU = 8192
-ALGO_BYTES_PER_CELL = 64  # DESIGN.md §4: 4 doubles read + 4 doubles written per cell update
+ALGO_BYTES_PER_CELL = 64  # DESIGN.md §3/§4: 4 doubles read + 4 doubles written per cell update
 METRIC = "Mcell-updates/s (fp64)"
 UNIT = "Mcell-updates/s"
 
@@ -205,27 +205,26 @@ def ours(args):
         launches = e2d.lib().e2d_kernel_launch_count() - launches0
         assert st.nStep == W + K
     else:
-        from euler2d_kokkos_b200.distributed import SlabRun
+        # one process per GPU; the library's own peer-memory loop (csrc/e2d_slab.cu): halo rows + CFL partials as
+        # direct NVLink stores, no NCCL call per step.  torch.distributed only all-gathers the CUDA IPC handles.
+        from euler2d_kokkos_b200.distributed import PeerSlabRun
 
-        run = SlabRun(hp, device=dev)
-        for _ in range(W):
-            run.step()
+        run = PeerSlabRun(hp, device=dev)
+        run.hydro.enable_timers(True)
+        run.run(W)
         barrier()
         launches0 = e2d.lib().e2d_kernel_launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clk:
-            ev0.record()
-            for _ in range(K):
-                run.step()
-            ev1.record()
+            st = run.run(W + K)
             barrier()
-        seconds = ev0.elapsed_time(ev1) * 1e-3
-        kernel_seconds = 0.0
+        seconds = st.seconds
+        kernel_seconds = st.seconds_step_kernel
         launches = e2d.lib().e2d_kernel_launch_count() - launches0
-        tmax = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        tmax = torch.tensor([seconds, kernel_seconds], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        seconds = float(tmax.item())
-        assert run.nStep == W + K
+        seconds, kernel_seconds = float(tmax[0].item()), float(tmax[1].item())
+        assert st.nStep == W + K
+        extra["halo_exchange"] = "peer stores over NVLink + system-scope flags (CUDA IPC), dt by max over per-rank slots"
 
     value = cells_total * K / seconds * 1e-6
 
@@ -240,7 +239,8 @@ def ours(args):
     roofline = None
     if kernel_seconds > 0:
         per_launch = kernel_seconds / K
-        achieved = ALGO_BYTES_PER_CELL * (hp.nx * hp.ny) / per_launch * 1e-9
+        cells_per_launch = NX_PER_GPU * NY_PER_GPU  # one launch = one GPU's slab
+        achieved = ALGO_BYTES_PER_CELL * cells_per_launch / per_launch * 1e-9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_fused_step_8192x8192")
@@ -249,7 +249,7 @@ def ours(args):
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                     "traffic": traffic, "kernel": "k_fused_step<HLLC, fused dt>", "kernel_ms_per_launch": per_launch * 1e3,
                     "kernel_share_of_step": kernel_seconds / seconds, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * hp.nx * hp.ny,
+                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_per_launch,
                     "note": "the strict fp64 step is FP64-issue bound, not HBM bound (DESIGN.md §4): ~700 FP64-pipe "
                             "instructions per cell vs 64 B"}
 

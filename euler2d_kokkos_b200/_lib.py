@@ -69,6 +69,13 @@ class RunStats(C.Structure):
                 ("launches", C.c_longlong), ("seconds_step_kernel", C.c_double)]
 
 
+class IpcBlob(C.Structure):
+    """Mirror of ``e2d_ipc_blob``: the CUDA IPC handles of one rank's U, U2 and comm block."""
+
+    _fields_ = [("U", C.c_ubyte * 64), ("U2", C.c_ubyte * 64), ("comm", C.c_ubyte * 64), ("rank", C.c_int),
+                ("nranks", C.c_int), ("ny_loc", C.c_int), ("device", C.c_int)]
+
+
 # every symbol include/euler2d_b200.h declares: name -> (restype, argtypes)
 _dp = C.POINTER(C.c_double)
 _pp = C.POINTER(Params)
@@ -102,6 +109,9 @@ SIGNATURES = {
     "e2d_godunov_unsplit": (C.c_int, [_vp, C.c_int, C.c_double]),
     "e2d_godunov_unsplit_nobc": (C.c_int, [_vp, C.c_int, C.c_double]),
     "e2d_run": (C.c_int, [_vp, C.c_long, C.POINTER(RunStats)]),
+    "e2d_ipc_export": (C.c_int, [_vp, C.POINTER(IpcBlob)]),
+    "e2d_ipc_connect": (C.c_int, [_vp, C.POINTER(IpcBlob), C.c_int]),
+    "e2d_peer_connect_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "e2d_get_dt_history": (C.c_int, [_vp, _dp, C.c_long, C.POINTER(C.c_long)]),
     "e2d_set_time": (C.c_int, [_vp, C.c_double, C.c_int]),
     "e2d_download": (C.c_int, [_vp, C.c_int, _vp, C.c_int]),

@@ -77,6 +77,22 @@ struct e2d_handle
   double *             d_hist = nullptr;
   long                 hist_cap = 0;
   bool                 loop_primed = false; // d_loop->invdt_cur valid for the current state
+  // the slab loop (e2d_slab.cu)
+  int                  device = 0;
+  SlabComm *           d_comm = nullptr;
+  SlabState *          d_state = nullptr;
+  SlabState *          h_state = nullptr; // pinned mirror
+  unsigned long long   seq = 0;           // steps issued through the slab loop so far (flags carry seq)
+  struct
+  {
+    bool       connected = false;
+    int        lower = -1, upper = -1; // neighbour ranks
+    double *   lowerU[2] = { nullptr, nullptr }; // the neighbours' U / U2 as peer pointers
+    double *   upperU[2] = { nullptr, nullptr };
+    int        lower_jsize = 0, upper_jsize = 0;
+    SlabComm * comm[kMaxRanks] = {};
+    std::vector<void *> ipc_opened;
+  } peers;
   double               t = 0.0;
   int                  nStep = 0;
   double               dt_last = 0.0;
@@ -530,6 +546,13 @@ extern "C"
       E2D_TRY(cudaMalloc(&h->d_bits, sizeof(unsigned long long)));
       E2D_TRY(cudaMalloc(&h->d_loop, sizeof(LoopState)));
       E2D_TRY(cudaMallocHost(&h->h_loop, sizeof(LoopState)));
+      E2D_TRY(cudaGetDevice(&h->device));
+      E2D_TRY(cudaMalloc(&h->d_comm, sizeof(SlabComm)));
+      E2D_TRY(cudaMemset(h->d_comm, 0, sizeof(SlabComm)));
+      E2D_TRY(cudaMalloc(&h->d_state, sizeof(SlabState)));
+      E2D_TRY(cudaMemset(h->d_state, 0, sizeof(SlabState)));
+      E2D_TRY(cudaMallocHost(&h->h_state, sizeof(SlabState)));
+      h->peers.comm[h->slab.rank < kMaxRanks ? h->slab.rank : 0] = h->d_comm;
       E2D_TRY(cudaEventCreate(&h->ev[0]));
       E2D_TRY(cudaEventCreate(&h->ev[1]));
       for (int k = 0; k < 5 && rc == E2D_OK; ++k)
@@ -563,6 +586,7 @@ extern "C"
   {
     if (!h)
       return E2D_OK;
+    cudaSetDevice(h->device);
     if (h->stream)
       cudaStreamSynchronize(h->stream);
     if (h->own_U)
@@ -576,6 +600,12 @@ extern "C"
     cudaFree(h->Sy);
     cudaFree(h->d_bits);
     cudaFree(h->d_loop);
+    for (void * q : h->peers.ipc_opened)
+      cudaIpcCloseMemHandle(q);
+    cudaFree(h->d_comm);
+    cudaFree(h->d_state);
+    if (h->h_state)
+      cudaFreeHost(h->h_state);
     cudaFree(h->d_hist);
     if (h->h_loop)
       cudaFreeHost(h->h_loop);
@@ -601,6 +631,7 @@ extern "C"
   {
     if (!h || !dt)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     const double * A = (useU == 0) ? h->U : h->U2; // HydroRun.h:237-240
     E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), h->stream));
     E2D_CUDA(launch_reduce_invdt(h->p, h->g, A, h->d_bits, h->stream));
@@ -618,6 +649,7 @@ extern "C"
   {
     if (!h || (which != E2D_U && which != E2D_U2))
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     E2D_CUDA(launch_make_boundaries(h->p, h->g, array_of(h, which), faces_for(h), nullptr, h->stream));
     return E2D_OK;
   }
@@ -627,6 +659,7 @@ extern "C"
   {
     if (!h)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     h->loop_primed = false;
     if (nStep % 2 == 0) // HydroRun.h:263-270
       return godunov_impl(h, h->U, h->U2, dt, true);
@@ -638,6 +671,7 @@ extern "C"
   {
     if (!h)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     h->loop_primed = false;
     if (nStep % 2 == 0)
       return godunov_impl(h, h->U, h->U2, dt, false);
@@ -649,10 +683,12 @@ extern "C"
   {
     if (!h)
       return fail(E2D_ERR_INVALID, "bad argument");
-    if (!h->whole)
-      return fail(E2D_ERR_UNSUPPORTED, "e2d_run drives a whole-domain handle; slabs are stepped by the caller");
+    const int nranks = h->slab.nranks, rank = h->slab.rank;
+    if (nranks > 1 && !h->peers.connected)
+      return fail(E2D_ERR_UNSUPPORTED, "e2d_run on a slab needs its peers: call e2d_ipc_connect / e2d_peer_connect_local");
     const e2d_params & p = h->p;
     cudaStream_t       st = h->stream;
+    E2D_CUDA(cudaSetDevice(h->device));
     if (max_steps < 0)
       max_steps = p.nStepmax;
     const unsigned long long launches0 = g_launches.load();
@@ -674,21 +710,48 @@ extern "C"
       h->hist_cap = cap;
     }
 
-    // prime the loop state: (t, nStep) from the handle, invDt of the current array (main.cpp:128)
-    h->h_loop->t = h->t;
-    h->h_loop->dt = h->dt_last;
-    h->h_loop->nStep = h->nStep;
-    h->h_loop->done = !(h->t < p.tEnd && h->nStep < max_steps);
-    h->h_loop->invdt_cur = 0;
-    h->h_loop->invdt_next = 0;
-    E2D_CUDA(cudaMemcpyAsync(h->d_loop, h->h_loop, sizeof(LoopState), cudaMemcpyHostToDevice, st));
+    // prime the loop state: (t, nStep) from the handle, invDt partial of the current array (main.cpp:128)
+    SlabState & hs = *h->h_state;
+    hs.t = h->t;
+    hs.dt = h->dt_last;
+    hs.invdt_acc = 0;
+    hs.nStep = h->nStep;
+    hs.done = !(h->t < p.tEnd && h->nStep < max_steps);
+    hs.pending = 0;
+    hs.error = 0;
+    E2D_CUDA(cudaMemcpyAsync(h->d_state, h->h_state, sizeof(SlabState), cudaMemcpyHostToDevice, st));
     {
       const double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
-      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, &h->d_loop->invdt_cur, st));
+      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, &h->d_state->invdt_acc, st));
     }
 
+    SlabStepArgs sa;
+    sa.mine = h->d_comm;
+    sa.st = h->d_state;
+    sa.has_lower = h->peers.lower >= 0;
+    sa.has_upper = h->peers.upper >= 0;
+    sa.nranks = nranks;
+    sa.cfl = p.cfl;
+    sa.tEnd = p.tEnd;
+    sa.max_steps = (int)max_steps;
+    sa.dt_hist = h->d_hist;
+    sa.hist_cap = h->hist_cap;
+    SlabPushArgs pa;
+    pa.isize = h->g.isize;
+    pa.jsize = h->g.jsize;
+    pa.lower_jsize = h->peers.lower_jsize;
+    pa.upper_jsize = h->peers.upper_jsize;
+    for (int k = 0; k < kMaxRanks; ++k)
+      pa.comm[k] = h->peers.comm[k];
+    pa.st = h->d_state;
+    pa.nranks = nranks;
+    pa.rank = rank;
+    pa.lower = h->peers.lower;
+    pa.upper = h->peers.upper;
+    const int faces = faces_for(h);
+
     E2D_CUDA(cudaEventRecord(h->ev[0], st));
-    int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when kernels no-op
+    int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when the step is a no-op
     const int batch = 64;
     double    step_kernel_ms = 0.0;
     if (h->timing && h->ev_step.empty())
@@ -697,7 +760,9 @@ extern "C"
       for (auto & e : h->ev_step)
         E2D_CUDA(cudaEventCreate(&e));
     }
-    bool      finished = h->h_loop->done != 0;
+    // Every rank must issue the same number of steps (the flags count them): `done` is computed from identical
+    // data on every rank and looked at after the same batches, so all ranks stop together.
+    bool finished = hs.done != 0;
     while (!finished)
     {
       long todo = max_steps - n_host;
@@ -705,19 +770,29 @@ extern "C"
         todo = batch;
       for (long k = 0; k < todo; ++k, ++n_host)
       {
-        double * in = (n_host % 2 == 0) ? h->U : h->U2;
-        double * out = (n_host % 2 == 0) ? h->U2 : h->U;
-        E2D_CUDA(launch_loop_begin_step(h->d_loop, p.cfl, p.tEnd, st));
-        E2D_CUDA(launch_make_boundaries(p, h->g, in, E2D_FACES_ALL, &h->d_loop->done, st));
+        const int which = n_host % 2; // 0: U -> U2
+        double *  in = which == 0 ? h->U : h->U2;
+        double *  out = which == 0 ? h->U2 : h->U;
+        h->seq += 1;
+        sa.seq = pa.seq = h->seq;
+        sa.parity = pa.parity = (int)(h->seq & 1);
+        if (nranks > 1)
+        {
+          pa.A = in;
+          pa.lowerA = h->peers.lower >= 0 ? h->peers.lowerU[which] : nullptr;
+          pa.upperA = h->peers.upper >= 0 ? h->peers.upperU[which] : nullptr;
+          E2D_CUDA(launch_slab_push(pa, st));
+        }
+        E2D_CUDA(launch_slab_boundaries(p, h->g, in, faces, sa, st));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
-        E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_loop->dt, &h->d_loop->invdt_next,
-                                   &h->d_loop->done, st));
+        E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_state->dt, &h->d_state->invdt_acc, &h->d_state->done,
+                                   st));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));
-        E2D_CUDA(launch_loop_end_step(h->d_loop, p.tEnd, (int)max_steps, h->d_hist, h->hist_cap, st));
       }
-      E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+      E2D_CUDA(launch_slab_finish(sa, st)); // closes the last opened step (a no-op for the next batch's first step)
+      E2D_CUDA(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(SlabState), cudaMemcpyDeviceToHost, st));
       E2D_CUDA(cudaStreamSynchronize(st));
       if (h->timing)
         for (long k = 0; k < todo; ++k)
@@ -726,17 +801,17 @@ extern "C"
           E2D_CUDA(cudaEventElapsedTime(&ms_k, h->ev_step[2 * k], h->ev_step[2 * k + 1]));
           step_kernel_ms += ms_k;
         }
-      finished = h->h_loop->done != 0 || n_host >= max_steps;
+      if (hs.error)
+        return fail(E2D_ERR_CUDA, "slab loop: timed out waiting for a peer GPU (did a rank die?)");
+      finished = hs.done != 0 || n_host >= max_steps;
     }
     E2D_CUDA(cudaEventRecord(h->ev[1], st));
-    E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
     E2D_CUDA(cudaEventSynchronize(h->ev[1]));
-    E2D_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     E2D_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    h->t = h->h_loop->t;
-    h->nStep = h->h_loop->nStep;
-    h->dt_last = h->h_loop->dt;
+    h->t = hs.t;
+    h->nStep = hs.nStep;
+    h->dt_last = hs.dt;
     if (stats)
     {
       stats->nStep = h->nStep;
@@ -749,11 +824,152 @@ extern "C"
     return E2D_OK;
   }
 
+  // ------------------------------------------------------------------ peers of a slab (NVLink peer memory)
+  static void
+  neighbours_of(const e2d_handle * h, int & lower, int & upper)
+  {
+    const int r = h->slab.rank, n = h->slab.nranks;
+    lower = r > 0 ? r - 1 : (h->p.boundary_type_ymin == E2D_BC_PERIODIC ? n - 1 : -1);
+    upper = r < n - 1 ? r + 1 : (h->p.boundary_type_ymax == E2D_BC_PERIODIC ? 0 : -1);
+    if (n == 1)
+      lower = upper = -1;
+  }
+
+  int
+  e2d_ipc_export(e2d_handle * h, e2d_ipc_blob * out)
+  {
+    if (!h || !out)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= E2D_IPC_HANDLE_BYTES, "handle size");
+    std::memset(out, 0, sizeof *out);
+    E2D_CUDA(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t m;
+    E2D_CUDA(cudaIpcGetMemHandle(&m, h->U));
+    std::memcpy(out->U, &m, sizeof m);
+    E2D_CUDA(cudaIpcGetMemHandle(&m, h->U2));
+    std::memcpy(out->U2, &m, sizeof m);
+    E2D_CUDA(cudaIpcGetMemHandle(&m, h->d_comm));
+    std::memcpy(out->comm, &m, sizeof m);
+    out->rank = h->slab.rank;
+    out->nranks = h->slab.nranks;
+    out->ny_loc = h->slab.ny_loc;
+    out->device = h->device;
+    return E2D_OK;
+  }
+
+  int
+  e2d_ipc_connect(e2d_handle * h, const e2d_ipc_blob * blobs, int nranks)
+  {
+    if (!h || !blobs || nranks != h->slab.nranks || nranks > kMaxRanks)
+      return fail(E2D_ERR_INVALID, "bad argument (nranks must match the slab and be <= 16)");
+    E2D_CUDA(cudaSetDevice(h->device));
+    int lower, upper;
+    neighbours_of(h, lower, upper);
+    auto open = [&](const unsigned char * raw, void ** ptr) -> cudaError_t {
+      cudaIpcMemHandle_t m;
+      std::memcpy(&m, raw, sizeof m);
+      cudaError_t e = cudaIpcOpenMemHandle(ptr, m, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess)
+        h->peers.ipc_opened.push_back(*ptr);
+      return e;
+    };
+    const int me = h->slab.rank;
+    for (int k = 0; k < nranks; ++k)
+    {
+      if (blobs[k].rank != k || blobs[k].nranks != nranks)
+        return fail(E2D_ERR_INVALID, "blobs must be in rank order");
+      if (k == me)
+      {
+        h->peers.comm[k] = h->d_comm;
+        continue;
+      }
+      void * c = nullptr;
+      E2D_CUDA(open(blobs[k].comm, &c));
+      h->peers.comm[k] = static_cast<SlabComm *>(c);
+    }
+    void *lU = nullptr, *lU2 = nullptr;
+    if (lower >= 0)
+    {
+      E2D_CUDA(open(blobs[lower].U, &lU));
+      E2D_CUDA(open(blobs[lower].U2, &lU2));
+      h->peers.lowerU[0] = static_cast<double *>(lU);
+      h->peers.lowerU[1] = static_cast<double *>(lU2);
+      h->peers.lower_jsize = blobs[lower].ny_loc + 2 * h->p.ghostWidth;
+    }
+    if (upper >= 0)
+    {
+      if (upper == lower)
+      { // two ranks with a periodic wrap: one peer is both neighbours (an IPC handle can be opened only once)
+        h->peers.upperU[0] = h->peers.lowerU[0];
+        h->peers.upperU[1] = h->peers.lowerU[1];
+      }
+      else
+      {
+        void *uU = nullptr, *uU2 = nullptr;
+        E2D_CUDA(open(blobs[upper].U, &uU));
+        E2D_CUDA(open(blobs[upper].U2, &uU2));
+        h->peers.upperU[0] = static_cast<double *>(uU);
+        h->peers.upperU[1] = static_cast<double *>(uU2);
+      }
+      h->peers.upper_jsize = blobs[upper].ny_loc + 2 * h->p.ghostWidth;
+    }
+    h->peers.lower = lower;
+    h->peers.upper = upper;
+    h->peers.connected = true;
+    return E2D_OK;
+  }
+
+  int
+  e2d_peer_connect_local(e2d_handle ** hs, int n)
+  {
+    if (!hs || n < 1 || n > kMaxRanks)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    for (int r = 0; r < n; ++r)
+      if (!hs[r] || hs[r]->slab.rank != r || hs[r]->slab.nranks != n)
+        return fail(E2D_ERR_INVALID, "handles must be the n slabs of one run, in rank order");
+    for (int r = 0; r < n; ++r)
+    {
+      e2d_handle * h = hs[r];
+      E2D_CUDA(cudaSetDevice(h->device));
+      for (int k = 0; k < n; ++k)
+      {
+        h->peers.comm[k] = hs[k]->d_comm;
+        if (k != r && hs[k]->device != h->device)
+        {
+          cudaError_t e = cudaDeviceEnablePeerAccess(hs[k]->device, 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled)
+            cudaGetLastError();
+          else if (e != cudaSuccess)
+            return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+        }
+      }
+      int lower, upper;
+      neighbours_of(h, lower, upper);
+      if (lower >= 0)
+      {
+        h->peers.lowerU[0] = hs[lower]->U;
+        h->peers.lowerU[1] = hs[lower]->U2;
+        h->peers.lower_jsize = hs[lower]->g.jsize;
+      }
+      if (upper >= 0)
+      {
+        h->peers.upperU[0] = hs[upper]->U;
+        h->peers.upperU[1] = hs[upper]->U2;
+        h->peers.upper_jsize = hs[upper]->g.jsize;
+      }
+      h->peers.lower = lower;
+      h->peers.upper = upper;
+      h->peers.connected = true;
+    }
+    return E2D_OK;
+  }
+
   int
   e2d_get_dt_history(e2d_handle * h, double * dts, long n_cap, long * n)
   {
     if (!h || !dts || !n)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     long cnt = h->nStep < h->hist_cap ? h->nStep : h->hist_cap;
     if (cnt > n_cap)
       cnt = n_cap;
@@ -784,6 +1000,7 @@ extern "C"
     double * A = h ? array_of(h, which) : nullptr;
     if (!A || !host)
       return fail(E2D_ERR_INVALID, "bad argument (array not allocated?)");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     if (layout == E2D_LAYOUT_SOA)
     {
       E2D_CUDA(cudaMemcpyAsync(host, A, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -805,6 +1022,7 @@ extern "C"
     double * A = h ? array_of(h, which) : nullptr;
     if (!A || !host)
       return fail(E2D_ERR_INVALID, "bad argument (array not allocated?)");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     h->loop_primed = false;
     if (layout == E2D_LAYOUT_SOA)
     {
@@ -838,6 +1056,7 @@ extern "C"
   {
     if (!h)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     E2D_CUDA(cudaStreamSynchronize(h->stream));
     return E2D_OK;
   }
@@ -856,6 +1075,7 @@ extern "C"
   {
     if (!h || !U_host_in || !U_host_out)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     const e2d_params & p = h->p;
     cudaStream_t       st = h->stream;
     const size_t       bytes = h->n * sizeof(double);
@@ -892,6 +1112,7 @@ extern "C"
     double * A = h ? array_of(h, which) : nullptr;
     if (!A)
       return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     const e2d_params &  p = h->p;
     std::vector<double> host(h->n);
     E2D_CUDA(cudaMemcpyAsync(host.data(), A, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -29,6 +29,62 @@ struct LoopState
   int                done;
 };
 
+// ---- the slab loop (e2d_slab.cu): state and peer links, all in device memory ----
+constexpr int kMaxRanks = 16;
+
+// written by the peers (and by this rank's own push): one block per rank, cudaMalloc'ed so that it can be shared
+// through CUDA IPC
+struct SlabComm
+{
+  unsigned long long invdt_slot[2][kMaxRanks]; // [step parity][rank]: bit pattern of that rank's invDt partial
+  unsigned long long invdt_flag[kMaxRanks];    // step+1 of the last partial rank k published here
+  unsigned long long halo_flag[2];             // step+1 of the last halo stored by the lower [0] / upper [1] neighbour
+  unsigned int       push_blocks_done;         // last-block election of this rank's own push kernel
+  unsigned int       pad_;
+};
+
+struct SlabState
+{
+  double             t;
+  double             dt;
+  unsigned long long invdt_acc; // accumulated by the fused step (atomicMax on the bit pattern)
+  int                nStep;
+  int                done;
+  int                pending; // dt of an opened step not yet added to t
+  int                error;   // a wait for a peer timed out
+};
+
+struct SlabPushArgs
+{
+  const double *    A; // the array the coming step reads
+  int               isize, jsize;
+  double *          lowerA; // the same-parity array of the lower / upper neighbour (peer pointers), or nullptr
+  double *          upperA;
+  int               lower_jsize, upper_jsize;
+  SlabComm *        comm[kMaxRanks]; // every rank's comm block (comm[rank] is local)
+  const SlabState * st;
+  int               nranks, rank, lower, upper; // neighbour ranks or -1
+  int               parity;
+  unsigned long long seq; // step + 1
+};
+
+struct SlabStepArgs
+{
+  SlabComm *         mine;
+  SlabState *        st;
+  unsigned long long seq;
+  int                has_lower, has_upper, nranks, parity;
+  double             cfl, tEnd;
+  int                max_steps;
+  double *           dt_hist;
+  long               hist_cap;
+};
+
+cudaError_t launch_slab_push(const SlabPushArgs & a, cudaStream_t st);
+cudaError_t launch_slab_boundaries(const e2d_params & p, const Geom & g, double * A, int faces, const SlabStepArgs & a,
+                                   cudaStream_t st);
+cudaError_t launch_slab_finish(const SlabStepArgs & a, cudaStream_t st);
+
 Settings make_settings(const e2d_params & p);
 Geom     make_geom(const e2d_params & p, int jsize_loc, int j_off);
 

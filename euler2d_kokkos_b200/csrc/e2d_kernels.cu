@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "e2d_bc.cuh"
 #include "e2d_internal.h"
 #include "e2d_march.cuh" // includes e2d_lean.cuh
 
@@ -173,103 +174,14 @@ k_init_problem(Geom g, InitArgs a, double * __restrict__ U, unsigned long long *
 }
 
 // ------------------------------------------------------------------------------------------
-// Boundary fill: the four MakeBoundariesFunctor<face> launches of HydroRun::make_boundaries
-// (src/HydroRunFunctors.h:1832-2030, src/HydroRun.h:390-399) as ONE launch.
-//
-// The reference runs XMIN, XMAX over all rows and then YMIN, YMAX over all columns, so a corner
-// ghost ends up as  (U(i0, j0) * sign_x) * sign_y.  Every source cell (i0, j0) is an interior cell,
-// which no pass writes, so each ghost cell can be produced independently by composing the two
-// index maps — same values, same signs (multiplying by +-1.0 is exact), no ordering between threads.
+// Boundary fill (e2d_bc.cuh): the four MakeBoundariesFunctor<face> launches as ONE launch
 // ------------------------------------------------------------------------------------------
-struct BcArgs
-{
-  int bc_xmin, bc_xmax, bc_ymin, bc_ymax;
-  int faces;
-};
-
-__device__ __forceinline__ int
-bc_source_lo(int bc, int k, int n, double & sign, bool is_normal)
-{ // ghost index k in {0,1}; :1893-1906 / :1968-1981
-  if (bc == E2D_BC_DIRICHLET)
-  {
-    if (is_normal)
-      sign = -1.0;
-    return 3 - k;
-  }
-  if (bc == E2D_BC_NEUMANN)
-    return 2;
-  return n + k; // periodic
-}
-
-__device__ __forceinline__ int
-bc_source_hi(int bc, int k, int n, double & sign, bool is_normal)
-{ // ghost index k in {n+2, n+3}; :1931-1944 / :2006-2019
-  if (bc == E2D_BC_DIRICHLET)
-  {
-    if (is_normal)
-      sign = -1.0;
-    return 2 * n + 3 - k;
-  }
-  if (bc == E2D_BC_NEUMANN)
-    return n + 1;
-  return k - n; // periodic
-}
-
 __global__ void __launch_bounds__(128)
 k_make_boundaries(Geom g, BcArgs a, double * __restrict__ U, const int * __restrict__ d_done)
 {
   if (d_done && *d_done)
     return;
-  const int    nx = g.nx, ny = g.ny;
-  const size_t plane = (size_t)g.isize * g.jsize;
-  const int    k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int    n_y = 4 * g.isize; // y-ghost rows, full width (i fastest)
-  const int    n_x = 4 * g.jsize; // x-ghost columns
-
-  int  i, j;
-  bool in_x_ghost, in_y_ghost;
-  if (k < n_y)
-  {
-    const int gsel = k / g.isize;
-    i = k - gsel * g.isize;
-    j = gsel < 2 ? gsel : ny + gsel;
-    if (!(a.faces & (gsel < 2 ? E2D_FACES_YMIN : E2D_FACES_YMAX)))
-      return;
-  }
-  else if (k < n_y + n_x)
-  {
-    const int kk = k - n_y;
-    j = kk >> 2;
-    const int gsel = kk & 3;
-    i = gsel < 2 ? gsel : nx + gsel;
-    if (!(a.faces & (gsel < 2 ? 1 : 2)))
-      return;
-    // rows that an active y face rewrites are produced by the first branch
-    if ((j < 2 && (a.faces & E2D_FACES_YMIN)) || (j >= ny + 2 && (a.faces & E2D_FACES_YMAX)))
-      return;
-  }
-  else
-    return;
-
-  in_x_ghost = (i < 2 && (a.faces & 1)) || (i >= nx + 2 && (a.faces & 2));
-  in_y_ghost = (j < 2 && (a.faces & E2D_FACES_YMIN)) || (j >= ny + 2 && (a.faces & E2D_FACES_YMAX));
-
-#pragma unroll
-  for (int v = 0; v < 4; ++v)
-  {
-    double sx = 1.0, sy = 1.0;
-    int    i0 = i, j0 = j;
-    if (in_x_ghost)
-      i0 = (i < 2) ? bc_source_lo(a.bc_xmin, i, nx, sx, v == IU) : bc_source_hi(a.bc_xmax, i, nx, sx, v == IU);
-    if (in_y_ghost)
-      j0 = (j < 2) ? bc_source_lo(a.bc_ymin, j, ny, sy, v == IV) : bc_source_hi(a.bc_ymax, j, ny, sy, v == IV);
-    double val = U[(size_t)i0 + (size_t)g.isize * j0 + v * plane];
-    if (in_x_ghost)
-      val = val * sx;
-    if (in_y_ghost)
-      val = val * sy;
-    U[(size_t)i + (size_t)g.isize * j + v * plane] = val;
-  }
+  bc_fill_cell(g, a, U, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -838,13 +750,8 @@ cudaError_t
 launch_make_boundaries(const e2d_params & p, const Geom & g, double * U, int faces, const int * d_done,
                        cudaStream_t st)
 {
-  BcArgs a;
-  a.bc_xmin = p.boundary_type_xmin;
-  a.bc_xmax = p.boundary_type_xmax;
-  a.bc_ymin = p.boundary_type_ymin;
-  a.bc_ymax = p.boundary_type_ymax;
-  a.faces = faces;
-  const int n = 4 * g.isize + 4 * g.jsize;
+  const BcArgs a = make_bc_args(p, faces);
+  const int    n = 4 * g.isize + 4 * g.jsize;
   k_make_boundaries<<<(n + 127) / 128, 128, 0, st>>>(g, a, U, d_done);
   count_launch();
   return cudaGetLastError();

@@ -107,6 +107,68 @@ class CudaEngine:
                                      self._stream()), "e2d_k_fused_step")
 
 
+class PeerSlabRun:
+    """HydroRun for one y-slab of a multi-process run, stepped by the library's own device-resident loop
+    (csrc/e2d_slab.cu): halo rows and CFL partials travel as direct stores into the neighbours' memory over NVLink
+    (CUDA IPC peer pointers) with system-scope flags — no NCCL call and no host round trip per step.
+    ``torch.distributed`` is used once, to all-gather the IPC handles."""
+
+    def __init__(self, params: HydroParams, rank: int | None = None, world: int | None = None,
+                 device: torch.device | None = None, group=None):
+        from .hydro_run import HydroRun
+
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.params = params
+        self.geo = slab_geometry(params, self.rank, self.world)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        slab = Slab(self.rank, self.world, self.geo.ny_loc, self.geo.j_off)
+        self.hydro = HydroRun(params, slab=slab)
+        if self.world > 1:
+            blob = _lib.IpcBlob()
+            check(lib().e2d_ipc_export(self.hydro._h, C.byref(blob)), "e2d_ipc_export")
+            mine = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).to(self.device)
+            allb = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allb, mine, group=self.group)
+            blobs = (_lib.IpcBlob * self.world)()
+            for r, tb in enumerate(allb):
+                raw = bytes(tb.cpu().numpy().tobytes())
+                C.memmove(C.byref(blobs[r]), raw, C.sizeof(_lib.IpcBlob))
+            check(lib().e2d_ipc_connect(self.hydro._h, blobs, self.world), "e2d_ipc_connect")
+            dist.barrier(group=self.group)  # every rank has mapped its peers before anyone stores into them
+
+    def run(self, max_steps: int):
+        """Steps until nStep == max_steps or t >= tEnd (every rank must pass the same max_steps)."""
+        return self.hydro.run(max_steps)
+
+    def current(self, nStep: int) -> torch.Tensor:
+        """This rank's slab [4][ny_loc+4][isize] after nStep steps, as a host tensor."""
+        import numpy as np
+
+        return torch.from_numpy(np.ascontiguousarray(self.hydro.download(nStep % 2)))
+
+    def gather_interior(self, nStep: int) -> torch.Tensor | None:
+        """Rank 0 receives the global interior [4][ny][nx] (tests / output)."""
+        mine = self.current(nStep)[:, 2:-2, 2:-2].contiguous().to(self.device)
+        if self.world == 1:
+            return mine
+        counts, _ = partition_rows(self.params.ny, self.world)
+        if self.rank == 0:
+            parts = [mine]
+            for r in range(1, self.world):
+                buf = torch.empty((4, counts[r], self.params.nx), dtype=torch.float64, device=self.device)
+                dist.recv(buf, r, self.group)
+                parts.append(buf)
+            return torch.cat(parts, dim=1)
+        dist.send(mine, 0, self.group)
+        return None
+
+    def close(self):
+        self.hydro.close()
+
+
 class SlabRun:
     """HydroRun for one y-slab of a multi-process run (same driver surface: compute_dt / make_boundaries /
     godunov_unsplit semantics folded into ``step``/``run``)."""

@@ -222,8 +222,27 @@ typedef struct e2d_run_stats
 /* The main loop of src/main.cpp:100-143 with IO off, device-resident: dt, t and nStep live in
  * device memory, one fused kernel per step (boundary fill, step, next-step CFL reduction), no
  * host synchronisation inside.  Continues from the handle's current (t, nStep); stops when
- * t >= tEnd or nStep >= max_steps (max_steps < 0: params.nStepmax).  Whole-domain handles only. */
+ * t >= tEnd or nStep >= max_steps (max_steps < 0: params.nStepmax).  Whole-domain handles, or slabs whose peers
+ * are connected (below). */
 int e2d_run(e2d_handle * h, long max_steps, e2d_run_stats * stats);
+/* ---- multi-GPU: e2d_run on y-slabs, halo rows and CFL partials as plain stores into peer memory over NVLink ----
+ * Each rank creates its slab handle (e2d_create with an e2d_slab; the library cudaMalloc's U/U2), the ranks connect
+ * to each other ONCE, then every rank calls e2d_run with the same max_steps: per step the ranks exchange the two
+ * boundary rows and their invDt partial by direct stores + system-scope flags (no NCCL call, no host round trip),
+ * and the result is bitwise identical to the single-GPU run (csrc/e2d_slab.cu).
+ *   one process per GPU (torchrun):  e2d_ipc_export -> all-gather the blobs by any means -> e2d_ipc_connect
+ *   one process, several GPUs:       e2d_peer_connect_local (then drive each handle from its own host thread:
+ *                                    e2d_run blocks while the ranks wait for each other on the device) */
+#define E2D_IPC_HANDLE_BYTES 64
+typedef struct e2d_ipc_blob
+{
+  unsigned char U[E2D_IPC_HANDLE_BYTES], U2[E2D_IPC_HANDLE_BYTES], comm[E2D_IPC_HANDLE_BYTES]; /* cudaIpcMemHandle_t */
+  int           rank, nranks, ny_loc, device;
+} e2d_ipc_blob;
+int e2d_ipc_export(e2d_handle * h, e2d_ipc_blob * out);
+int e2d_ipc_connect(e2d_handle * h, const e2d_ipc_blob * blobs /* nranks entries, rank order */, int nranks);
+int e2d_peer_connect_local(e2d_handle ** handles /* nranks entries, rank order */, int nranks);
+
 /* dt used by each step taken through e2d_run so far (n_cap entries max); returns count in *n */
 int e2d_get_dt_history(e2d_handle * h, double * dts, long n_cap, long * n);
 /* reset (t, nStep) bookkeeping of e2d_run, e.g. after e2d_upload */
