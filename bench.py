@@ -241,17 +241,29 @@ def ours(args):
         per_launch = kernel_seconds / K
         cells_per_launch = NX_PER_GPU * NY_PER_GPU  # one launch = one GPU's slab
         achieved = ALGO_BYTES_PER_CELL * cells_per_launch / per_launch * 1e-9
-        traffic = None
+        traffic, prof = None, {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_fused_step_8192x8192")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = prof.get("k_fused_step_8192x8192")
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                     "traffic": traffic, "kernel": "k_fused_step<HLLC, fused dt>", "kernel_ms_per_launch": per_launch * 1e3,
                     "kernel_share_of_step": kernel_seconds / seconds, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_per_launch,
-                    "note": "the strict fp64 step is FP64-issue bound, not HBM bound (DESIGN.md §4): ~700 FP64-pipe "
-                            "instructions per cell vs 64 B"}
+                    "note": "the strict fp64 step is FP64-pipe / issue bound, not HBM bound (DESIGN.md section 4): ~500 "
+                            "FP64-pipe warp instructions per 32 cells against 64 B per cell"}
+        # the resource that actually binds: FP64 pipe occupancy = (FP64 warp instructions per launch, counted by ncu)
+        # / (launch time x 592 SM sub-partitions x SM clock) against the pipe rate measured by tools/microbench
+        n_fp64 = prof.get("k_fused_step_8192x8192_fp64_warp_inst")
+        if n_fp64:
+            mhz = (clk.summary().get("sm_mhz") or 1965)
+            rate = n_fp64 / per_launch / (148 * 4) / (mhz * 1e6)
+            peak_rate = float(prof.get("fp64_peak_warp_inst_per_clk_per_smsp", 0.476))
+            roofline["fp64_pipe"] = {"warp_inst_per_launch": n_fp64, "achieved_per_clk_per_smsp": rate,
+                                     "peak_per_clk_per_smsp": peak_rate, "frac": rate / peak_rate, "sm_mhz": mhz,
+                                     "source": "ncu instruction count (profiles/) / live CUDA-event time; peak measured "
+                                               "by tools/microbench/fp64_peak.cu"}
 
     # ---------------- e2e through the host-buffer entry point (rank-local slab; N=1 only for now)
     e2e = None

@@ -749,6 +749,17 @@ extern "C"
     pa.lower = h->peers.lower;
     pa.upper = h->peers.upper;
     const int faces = faces_for(h);
+    FusedLink lk{};
+    if (nranks > 1)
+    {
+      lk.cnt = h->d_comm->fused_cnt;
+      lk.flag_lo = h->peers.lower >= 0 ? &h->peers.comm[h->peers.lower]->halo_flag[1] : nullptr; // I am its upper
+      lk.flag_hi = h->peers.upper >= 0 ? &h->peers.comm[h->peers.upper]->halo_flag[0] : nullptr; // I am its lower
+      for (int k = 0; k < kMaxRanks; ++k)
+        lk.comm[k] = h->peers.comm[k];
+      lk.nranks = nranks;
+      lk.rank = rank;
+    }
 
     E2D_CUDA(cudaEventRecord(h->ev[0], st));
     int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when the step is a no-op
@@ -762,6 +773,9 @@ extern "C"
     }
     // Every rank must issue the same number of steps (the flags count them): `done` is computed from identical
     // data on every rank and looked at after the same batches, so all ranks stop together.
+    // The flags of this call start one past anything an earlier call's last fused step may have published.
+    h->seq += 1;
+    bool first = true;
     bool finished = hs.done != 0;
     while (!finished)
     {
@@ -776,18 +790,33 @@ extern "C"
         h->seq += 1;
         sa.seq = pa.seq = h->seq;
         sa.parity = pa.parity = (int)(h->seq & 1);
-        if (nranks > 1)
-        {
+        if (nranks > 1 && first)
+        { // the call's first step: halo rows of the current array + the primed invDt partial, by a push kernel;
+          // every later step finds them already published by the previous fused step
           pa.A = in;
           pa.lowerA = h->peers.lower >= 0 ? h->peers.lowerU[which] : nullptr;
           pa.upperA = h->peers.upper >= 0 ? h->peers.upperU[which] : nullptr;
           E2D_CUDA(launch_slab_push(pa, st));
         }
+        first = false;
         E2D_CUDA(launch_slab_boundaries(p, h->g, in, faces, sa, st));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
-        E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_state->dt, &h->d_state->invdt_acc, &h->d_state->done,
-                                   st));
+        if (nranks > 1)
+        {
+          MarchPeers mp; // the step writes `out`: the array the NEXT step reads, on the neighbours too
+          mp.lo = h->peers.lower >= 0 ? h->peers.lowerU[1 - which] : nullptr;
+          mp.hi = h->peers.upper >= 0 ? h->peers.upperU[1 - which] : nullptr;
+          mp.lo_jsize = h->peers.lower_jsize;
+          mp.hi_jsize = h->peers.upper_jsize;
+          lk.seq_next = h->seq + 1;
+          lk.parity_next = (int)((h->seq + 1) & 1);
+          E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_state->dt, &h->d_state->invdt_acc,
+                                     &h->d_state->done, st, &mp, &lk));
+        }
+        else
+          E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_state->dt, &h->d_state->invdt_acc,
+                                     &h->d_state->done, st));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));
       }
@@ -825,6 +854,30 @@ extern "C"
   }
 
   // ------------------------------------------------------------------ peers of a slab (NVLink peer memory)
+  // everything e2d_run would otherwise do lazily (kernel loading, the dt-history allocation) and that could wait for
+  // a peer's spinning kernel when several ranks share a device
+  static int
+  prepare_slab_loop(e2d_handle * h)
+  {
+    E2D_CUDA(preload_slab_kernels());
+    E2D_CUDA(preload_step_kernels());
+    const long cap = (long)h->p.nStepmax + 128;
+    if (h->hist_cap < cap)
+    {
+      double * nh = nullptr;
+      E2D_CUDA(cudaMalloc(&nh, sizeof(double) * cap));
+      E2D_CUDA(cudaMemset(nh, 0, sizeof(double) * cap));
+      if (h->d_hist)
+      {
+        E2D_CUDA(cudaMemcpy(nh, h->d_hist, sizeof(double) * h->hist_cap, cudaMemcpyDeviceToDevice));
+        cudaFree(h->d_hist);
+      }
+      h->d_hist = nh;
+      h->hist_cap = cap;
+    }
+    return E2D_OK;
+  }
+
   static void
   neighbours_of(const e2d_handle * h, int & lower, int & upper)
   {
@@ -916,7 +969,7 @@ extern "C"
     h->peers.lower = lower;
     h->peers.upper = upper;
     h->peers.connected = true;
-    return E2D_OK;
+    return prepare_slab_loop(h);
   }
 
   int
@@ -960,6 +1013,8 @@ extern "C"
       h->peers.lower = lower;
       h->peers.upper = upper;
       h->peers.connected = true;
+      if (int rc = prepare_slab_loop(h))
+        return rc;
     }
     return E2D_OK;
   }

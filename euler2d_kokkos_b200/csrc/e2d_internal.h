@@ -40,7 +40,20 @@ struct SlabComm
   unsigned long long invdt_flag[kMaxRanks];    // step+1 of the last partial rank k published here
   unsigned long long halo_flag[2];             // step+1 of the last halo stored by the lower [0] / upper [1] neighbour
   unsigned int       push_blocks_done;         // last-block election of this rank's own push kernel
-  unsigned int       pad_;
+  unsigned int       fused_cnt[3];             // elections inside the fused step: lower-halo / upper-halo / all blocks
+};
+
+// what the fused step needs to publish its halo rows and its invDt partial itself (device pointers; by value)
+struct FusedLink
+{
+  unsigned int *       cnt;                     // -> SlabComm::fused_cnt of this rank
+  unsigned int         n_lo, n_hi, n_all;       // blocks holding rows {2,3} / the last two interior rows / all
+  unsigned long long * flag_lo;                 // lower neighbour's halo_flag[1], upper neighbour's halo_flag[0]
+  unsigned long long * flag_hi;
+  SlabComm *           comm[kMaxRanks];
+  int                  nranks, rank;
+  int                  parity_next;             // slot parity and flag value of the NEXT step
+  unsigned long long   seq_next;
 };
 
 struct SlabState
@@ -84,6 +97,8 @@ cudaError_t launch_slab_push(const SlabPushArgs & a, cudaStream_t st);
 cudaError_t launch_slab_boundaries(const e2d_params & p, const Geom & g, double * A, int faces, const SlabStepArgs & a,
                                    cudaStream_t st);
 cudaError_t launch_slab_finish(const SlabStepArgs & a, cudaStream_t st);
+cudaError_t preload_slab_kernels(); // force-load the loop's kernels (lazy loading may wait for running kernels)
+cudaError_t preload_step_kernels();
 
 Settings make_settings(const e2d_params & p);
 Geom     make_geom(const e2d_params & p, int jsize_loc, int j_off);
@@ -107,9 +122,16 @@ cudaError_t launch_trace_and_fluxes(const e2d_params & p, const Geom & g, const 
                                     cudaStream_t st);
 cudaError_t launch_update_dir(const e2d_params & p, const Geom & g, double * U, const double * F, int dir,
                               cudaStream_t st);
+struct MarchPeers
+{
+  double * lo = nullptr; // same-parity OUTPUT array of the lower / upper neighbour
+  double * hi = nullptr;
+  int      lo_jsize = 0, hi_jsize = 0;
+};
+// link/peers: nullptr for a single GPU or when the caller exchanges halos itself
 cudaError_t launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
                               const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done,
-                              cudaStream_t st);
+                              cudaStream_t st, const MarchPeers * peers = nullptr, FusedLink * link = nullptr);
 // scalar bookkeeping of the device-resident loop
 cudaError_t launch_loop_begin_step(LoopState * st_dev, double cfl, double tEnd, cudaStream_t st);
 cudaError_t launch_loop_end_step(LoopState * st_dev, double tEnd, int max_steps, double * dt_hist, long hist_cap,

@@ -416,27 +416,103 @@ k_update_dir(Geom g, double * __restrict__ U, const double * __restrict__ F)
 // ------------------------------------------------------------------------------------------
 // The fused step (e2d_march.cuh)
 // ------------------------------------------------------------------------------------------
-template <int SOLVER, bool FUSE_DT>
+__device__ __forceinline__ void
+st_release_sys_u64(unsigned long long * p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int SOLVER, bool FUSE_DT, bool LINKED>
 __global__ void __launch_bounds__(kBX, kMarchMinBlocks)
-k_fused_step(MarchArgs a, const int * __restrict__ d_done)
+k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
 {
   if (d_done && *d_done)
     return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MarchSmem<kBX> &                  sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
   MarchThread<kBX, SOLVER, FUSE_DT> th;
-  if (!th.init(a, sm, threadIdx.x, blockIdx.x, blockIdx.y))
-    return;
-  __syncthreads();
-  for (int r = th.j0 - 1; r <= th.j1; ++r)
+  // blockIdx.y -> row segment: with peers the two EDGE segments come first, so that the halo rows are on their way
+  // (and usually landed) while the interior is still being computed
+  int seg = blockIdx.y;
+  if (LINKED)
   {
-    th.phaseA(a, sm, r);
-    __syncthreads();
-    th.phaseB(a, sm, r);
+    const int nseg = gridDim.y;
+    seg = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? nseg - 1 : (int)blockIdx.y - 1);
   }
-  th.finish(a);
-  if (FUSE_DT && a.invdt_bits)
-    block_max_to_global(th.invdt, a.invdt_bits);
+  const bool active = th.init(a, sm, threadIdx.x, blockIdx.x, seg);
+  if (active)
+  {
+    __syncthreads();
+    for (int r = th.j0 - 1; r <= th.j1; ++r)
+    {
+      th.phaseA(a, sm, r);
+      __syncthreads();
+      th.phaseB(a, sm, r);
+    }
+    th.finish(a);
+    if (FUSE_DT && a.invdt_bits)
+      block_max_to_global(th.invdt, a.invdt_bits);
+  }
+  if (LINKED)
+  {
+    const bool lo = active && a.peer_lo && th.j0 <= 3 && th.j1 > 2;
+    const bool hi = active && a.peer_hi && th.j0 <= a.jsize - 3 && th.j1 > a.jsize - 4;
+    // Edge segments: every thread copies the edge rows of ITS column (which it stored itself a moment ago: program
+    // order makes them visible to it) into the neighbour's ghost rows of the same-parity array.
+    if ((lo || hi) && th.store)
+    {
+      const size_t plane = (size_t)a.isize * a.jsize;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        // k = 0, 1: my rows 2, 3 -> the lower neighbour's top ghost rows
+        // k = 2, 3: my last two interior rows -> the upper neighbour's rows 0, 1
+        const bool to_lo = k < 2;
+        const int  jr = to_lo ? 2 + k : a.jsize - 4 + (k - 2);
+        if (!(to_lo ? lo : hi) || jr < th.j0 || jr >= th.j1)
+          continue;
+        const double * src = a.Uout + (jr * a.isize + th.i);
+        const int      jsize_d = to_lo ? a.peer_lo_jsize : a.peer_hi_jsize;
+        const int      jd = to_lo ? jsize_d - 2 + k : k - 2;
+        double *       dst = (to_lo ? a.peer_lo : a.peer_hi) + (jd * a.isize + th.i);
+        const size_t   plane_d = (size_t)a.isize * jsize_d;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          dst[v * plane_d] = src[v * plane];
+      }
+    }
+    // Publication (e2d_slab.cu): every block fences its stores (peer rows, atomicMax), then three elections by
+    // arrival count.  The last block holding the lower / upper edge rows raises the neighbour's halo flag; the
+    // last block of the grid copies the finished invDt partial into every rank's slot and raises the invDt flags.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      if (lo && atomicAdd(&link.cnt[0], 1u) == link.n_lo - 1)
+      {
+        link.cnt[0] = 0;
+        __threadfence_system();
+        st_release_sys_u64(link.flag_lo, link.seq_next);
+      }
+      if (hi && atomicAdd(&link.cnt[1], 1u) == link.n_hi - 1)
+      {
+        link.cnt[1] = 0;
+        __threadfence_system();
+        st_release_sys_u64(link.flag_hi, link.seq_next);
+      }
+      if (atomicAdd(&link.cnt[2], 1u) == link.n_all - 1)
+      {
+        link.cnt[2] = 0;
+        __threadfence_system();
+        const unsigned long long part = atomicMax(a.invdt_bits, 0ull); // every block's atomicMax precedes its count
+        for (int k = 0; k < link.nranks; ++k)
+          link.comm[k]->invdt_slot[link.parity_next][link.rank] = part;
+        __threadfence_system();
+        for (int k = 0; k < link.nranks; ++k)
+          st_release_sys_u64(&link.comm[k]->invdt_flag[link.rank], link.seq_next);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -892,7 +968,8 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
 
 cudaError_t
 launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
-                  const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done, cudaStream_t st)
+                  const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done, cudaStream_t st,
+                  const MarchPeers * peers, FusedLink * link)
 {
   MarchArgs a;
   a.Uin = Uin;
@@ -910,28 +987,48 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
   const int  sol = solver_for(p);
   const bool fuse = d_invdt_bits != nullptr;
+  FusedLink  lk{};
+  if (link)
+  {
+    if (!fuse || !peers)
+      return cudaErrorInvalidValue;
+    a.peer_lo = peers->lo;
+    a.peer_hi = peers->hi;
+    a.peer_lo_jsize = peers->lo_jsize;
+    a.peer_hi_jsize = peers->hi_jsize;
+    // segments holding interior rows {0,1} / {ny-2, ny-1} (ny >= 2)
+    link->n_lo = (unsigned)nbx * (a.seg_rows == 1 ? 2u : 1u);
+    link->n_hi = (unsigned)nbx * (((g.ny - 2) / a.seg_rows != (g.ny - 1) / a.seg_rows) ? 2u : 1u);
+    link->n_all = (unsigned)nbx * (unsigned)nseg;
+    lk = *link;
+  }
   const size_t smem = sizeof(MarchSmem<kBX>);
-#define E2D_FS1(SOL, FUSE)                                                                                       \
-  do                                                                                                             \
-  {                                                                                                              \
-    static bool configured = false; /* per instantiation; benign race: setting the attribute is idempotent */   \
-    if (!configured)                                                                                             \
-    {                                                                                                            \
-      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           (int)smem);                                                           \
-      if (e != cudaSuccess)                                                                                      \
-        return e;                                                                                                \
-      configured = true;                                                                                         \
-    }                                                                                                            \
-    k_fused_step<SOL, FUSE><<<grid, kBX, smem, st>>>(a, d_done);                                                 \
+#define E2D_FS1(SOL, FUSE, LINKED)                                                                        \
+  do                                                                                                      \
+  {                                                                                                       \
+    static bool configured_on[64] = {}; /* per instantiation and device; benign race: idempotent */      \
+    int         dev_ = 0;                                                                                 \
+    cudaGetDevice(&dev_);                                                                                 \
+    bool & configured = configured_on[dev_ & 63];                                                         \
+    if (!configured)                                                                                      \
+    {                                                                                                     \
+      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE, LINKED>,                               \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+      if (e != cudaSuccess)                                                                               \
+        return e;                                                                                         \
+      configured = true;                                                                                  \
+    }                                                                                                     \
+    k_fused_step<SOL, FUSE, LINKED><<<grid, kBX, smem, st>>>(a, d_done, lk);                              \
   } while (0)
-#define E2D_FS(SOL)        \
-  do                       \
-  {                        \
-    if (fuse)              \
-      E2D_FS1(SOL, true);  \
-    else                   \
-      E2D_FS1(SOL, false); \
+#define E2D_FS(SOL)               \
+  do                              \
+  {                               \
+    if (link)                     \
+      E2D_FS1(SOL, true, true);   \
+    else if (fuse)                \
+      E2D_FS1(SOL, true, false);  \
+    else                          \
+      E2D_FS1(SOL, false, false); \
   } while (0)
   if (sol == 0)
     E2D_FS(0);
@@ -943,6 +1040,25 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
 #undef E2D_FS1
   count_launch();
   return cudaGetLastError();
+}
+
+cudaError_t
+preload_step_kernels()
+{
+  cudaFuncAttributes fa;
+  cudaError_t        e = cudaFuncGetAttributes(&fa, k_reduce_invdt);
+#define E2D_PRE(SOL)                                                      \
+  if (e == cudaSuccess)                                                   \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, true>);        \
+  if (e == cudaSuccess)                                                   \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, false>);       \
+  if (e == cudaSuccess)                                                   \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, false, false>);
+  E2D_PRE(0)
+  E2D_PRE(1)
+  E2D_PRE(2)
+#undef E2D_PRE
+  return e;
 }
 
 cudaError_t

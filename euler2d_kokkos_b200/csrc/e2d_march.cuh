@@ -58,6 +58,13 @@ struct MarchArgs
   double               dt;         // used when d_dt == nullptr
   const double *       d_dt;       // device-resident dt (optional)
   unsigned long long * invdt_bits; // optional: atomicMax target for the next step's CFL reduction
+  // multi-GPU (e2d_slab.cu): the same-parity OUTPUT arrays of the lower / upper y-neighbour as peer pointers.  The
+  // blocks that produce this slab's first / last two interior rows copy them into the neighbour's ghost rows
+  // (NVLink stores) as soon as their segment is done, so the halo exchange of the NEXT step rides on this kernel —
+  // overlapped with the interior segments — instead of following it (k_fused_step, e2d_kernels.cu).
+  double * peer_lo = nullptr;
+  double * peer_hi = nullptr;
+  int      peer_lo_jsize = 0, peer_hi_jsize = 0;
 };
 
 template <int BX>
@@ -358,7 +365,8 @@ struct MarchThread
       invdt = fmax(invdt, cflv); // fmax drops a NaN operand like the reference's reduction (:72)
     if (store && r >= j0 + 1)
     {
-      double * po = a.Uout + ((r - 1) * a.isize + i);
+      const int jr = r - 1;
+      double *  po = a.Uout + (jr * a.isize + i);
       E2D_UNROLL
       for (int v = 0; v < 4; ++v)
         po[v * plane] = un[v];

@@ -5,10 +5,13 @@
 //
 // One step n on every rank (A = the array the step reads, by the parity of n; all ranks are at the same n):
 //
-//   k_slab_push        (multi-GPU only)  my first / last two interior rows of A  ->  the neighbours' ghost rows of A;
-//                      my invDt partial (left in device memory by the previous fused step)  ->  slot [n&1][rank] of
-//                      EVERY rank; then, by the last block to finish and after a system fence, the flags
-//                      halo_flag / invdt_flag := n+1 in the receivers' memory.
+//   k_slab_push        (multi-GPU, FIRST step of an e2d_run call only)  my first / last two interior rows of A  ->
+//                      the neighbours' ghost rows of A; my invDt partial  ->  slot [n&1][rank] of EVERY rank; then,
+//                      by the last block to finish and after a system fence, the flags halo_flag / invdt_flag := n+1
+//                      in the receivers' memory.  For every later step the PREVIOUS fused step has already done all
+//                      of this itself: its edge segments are scheduled first and store their rows into the
+//                      neighbours' ghost rows as they produce them, and its last block publishes the invDt partial
+//                      (k_fused_step<.., LINKED>, e2d_kernels.cu) — the exchange overlaps the interior compute.
 //   k_slab_boundaries  waits (spinning on its OWN memory) for the neighbours' halo flags and — one thread — for all
 //                      invDt flags; fills the boundaries of A (x faces on all local rows incl. the received halo
 //                      rows, physical y faces where this rank owns them: SURVEY.md §8e order, bit-exact corners);
@@ -159,13 +162,15 @@ k_slab_boundaries(Geom g, BcArgs bc, double * __restrict__ A, SlabStepArgs a)
 {
   if (threadIdx.x == 0)
   {
-    if (a.has_lower)
+    // once the loop is over the fused steps are no-ops and publish nothing: there is nothing to wait for
+    const bool over = *(volatile int *)&a.st->done != 0;
+    if (a.has_lower && !over)
       wait_flag(&a.mine->halo_flag[0], a.seq, a.st);
-    if (a.has_upper)
+    if (a.has_upper && !over)
       wait_flag(&a.mine->halo_flag[1], a.seq, a.st);
     if (blockIdx.x == 0)
     {
-      if (a.nranks > 1)
+      if (a.nranks > 1 && !over)
         for (int k = 0; k < a.nranks; ++k)
           wait_flag(&a.mine->invdt_flag[k], a.seq, a.st);
       loop_scalars(a, true);
@@ -182,6 +187,21 @@ k_slab_finish(SlabStepArgs a)
 }
 
 } // namespace
+
+// CUDA loads kernels lazily, and loading may wait for running kernels: a rank whose boundary kernel is already
+// spinning on the device must never be the reason a peer's first launch cannot load.  Only matters when several
+// ranks share one device (tests), but costs nothing: resolve every kernel of the loop before the first step.
+cudaError_t
+preload_slab_kernels()
+{
+  cudaFuncAttributes fa;
+  cudaError_t        e = cudaFuncGetAttributes(&fa, k_slab_push);
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_slab_boundaries);
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_slab_finish);
+  return e;
+}
 
 cudaError_t
 launch_slab_push(const SlabPushArgs & a, cudaStream_t st)
