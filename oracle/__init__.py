@@ -53,6 +53,10 @@ class Params(C.Structure):
 
 _lib = None
 
+# The checker runs small grids: on a many-core GPU host an OpenMP team of 100+ threads spends its time in barriers
+# (the GPU test-suite took 30x longer on a 2-GPU box than on a 1-GPU one).  Cap the team unless the caller chose.
+os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 8)))
+
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when the reference tree is present)."""
