@@ -102,6 +102,9 @@ struct e2d_handle
   cudaEvent_t ev[2] = { nullptr, nullptr };
   cudaEvent_t ev_t[5][2] = {}; // one event pair per timer: the godunov timer nests the others
   std::vector<cudaEvent_t> ev_step; // e2d_run profiling: one pair per step of a batch
+  // e2d_step_host_streamed: copy streams and an event pool (created on first use)
+  cudaStream_t             s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace
@@ -620,6 +623,13 @@ extern "C"
     for (auto & e : h->ev_step)
       if (e)
         cudaEventDestroy(e);
+    for (auto & e : h->ev_pool)
+      if (e)
+        cudaEventDestroy(e);
+    if (h->s_in)
+      cudaStreamDestroy(h->s_in);
+    if (h->s_out)
+      cudaStreamDestroy(h->s_out);
     if (h->own_stream && h->stream)
       cudaStreamDestroy(h->stream);
     delete h;
@@ -1157,6 +1167,161 @@ extern "C"
     E2D_CUDA(cudaStreamSynchronize(st));
     if (dt_out)
       *dt_out = h->h_loop->dt;
+    h->loop_primed = false;
+    return E2D_OK;
+  }
+
+  // The step of a caller whose state lives in HOST memory, streamed: the rows travel host -> device in chunks, each
+  // chunk is advanced as soon as the two rows above it have landed, and finished chunks travel back while later
+  // ones are still arriving or being computed — H2D, the fused step and D2H overlap (full-duplex PCIe), so the call
+  // costs about one direction's transfer instead of two.  This needs dt BEFORE the rows are all there, which is
+  // exactly the reference's call structure: dt = compute_dt(); godunov_unsplit(nStep, dt) (src/main.cpp:128,139) —
+  // and the CFL reduction of the NEW state rides on the step, so the caller gets the next dt with the result.
+  int
+  e2d_step_host_streamed(e2d_handle * h, const double * U_host_in, double * U_host_out, double dt_in, int chunk_rows,
+                         double * dt_used, double * dt_next)
+  {
+    if (!h || !U_host_in || !U_host_out)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device);
+    const e2d_params & p = h->p;
+    const Geom &       g = h->g;
+    cudaStream_t       st = h->stream;
+    const int          isize = g.isize, jsize = g.jsize, ny = g.ny;
+    const size_t       plane = (size_t)isize * jsize;
+    const int          faces = faces_for(h);
+    if (!h->s_in)
+    {
+      E2D_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+      E2D_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    }
+    if (chunk_rows <= 0)
+      chunk_rows = (ny + 31) / 32; // ~32 chunks: the un-overlapped head and tail are ~2/32 of one direction
+    if (chunk_rows < 16)
+      chunk_rows = 16; // every chunk holds the source rows of the y faces next to it
+    const int nchunk = (ny + chunk_rows - 1) / chunk_rows;
+    while ((int)h->ev_pool.size() < 2 * nchunk + 4)
+    {
+      cudaEvent_t e;
+      E2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_pool.push_back(e);
+    }
+    cudaEvent_t * ev_in = h->ev_pool.data();           // [nchunk] chunk landed
+    cudaEvent_t * ev_cmp = h->ev_pool.data() + nchunk; // [nchunk] chunk advanced
+    cudaEvent_t   ev_start = h->ev_pool[2 * nchunk], ev_ymin = h->ev_pool[2 * nchunk + 1],
+                ev_fin = h->ev_pool[2 * nchunk + 2];
+    auto first_row = [&](int k) { return 2 + k * chunk_rows; };
+    auto last_row = [&](int k) { return (k == nchunk - 1) ? jsize - 2 : 2 + (k + 1) * chunk_rows; };
+    // rows [jlo, jhi) of all four planes
+    auto copy_rows = [&](double * dst, const double * src, int jlo, int jhi, cudaMemcpyKind kind, cudaStream_t s) {
+      for (int v = 0; v < 4; ++v)
+      {
+        const size_t    o = (size_t)jlo * isize + v * plane;
+        const cudaError_t e = cudaMemcpyAsync(dst + o, src + o, (size_t)(jhi - jlo) * isize * sizeof(double), kind, s);
+        if (e != cudaSuccess)
+          return e;
+      }
+      return cudaSuccess;
+    };
+
+    E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), st));
+    E2D_CUDA(cudaEventRecord(ev_start, st));
+    E2D_CUDA(cudaStreamWaitEvent(h->s_in, ev_start, 0));
+    E2D_CUDA(cudaStreamWaitEvent(h->s_out, ev_start, 0));
+
+    // ---- host -> device, in row order; a periodic YMIN face reads the LAST two interior rows: send those first
+    const bool early_top = (faces & E2D_FACES_YMIN) && p.boundary_type_ymin == E2D_BC_PERIODIC && nchunk > 1;
+    if (early_top)
+      E2D_CUDA(copy_rows(h->U, U_host_in, jsize - 4, jsize - 2, cudaMemcpyHostToDevice, h->s_in));
+    // (with early_top the last chunk rewrites those two rows, so it is enqueued only after the YMIN fill that reads
+    //  them has been — see below)
+    for (int k = 0; k < nchunk - (early_top ? 1 : 0); ++k)
+    {
+      const int jlo = k == 0 ? 0 : first_row(k), jhi = k == nchunk - 1 ? jsize : last_row(k);
+      E2D_CUDA(copy_rows(h->U, U_host_in, jlo, jhi, cudaMemcpyHostToDevice, h->s_in));
+      E2D_CUDA(cudaEventRecord(ev_in[k], h->s_in));
+    }
+
+    double dt = dt_in;
+    if (!(dt > 0.0))
+    {
+      // no dt from the caller: compute_dt needs every row, so only the step and the way back overlap
+      if (early_top)
+      {
+        const int k = nchunk - 1;
+        E2D_CUDA(copy_rows(h->U, U_host_in, first_row(k), jsize, cudaMemcpyHostToDevice, h->s_in));
+        E2D_CUDA(cudaEventRecord(ev_in[k], h->s_in));
+      }
+      E2D_CUDA(cudaStreamWaitEvent(st, ev_in[nchunk - 1], 0));
+      E2D_CUDA(launch_reduce_invdt(p, g, h->U, h->d_bits, st));
+      E2D_CUDA(cudaMemcpyAsync(&h->h_loop->invdt_cur, h->d_bits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), st));
+      E2D_CUDA(cudaStreamSynchronize(st));
+      double inv;
+      std::memcpy(&inv, &h->h_loop->invdt_cur, sizeof inv);
+      dt = p.cfl / inv; // HydroRun.h:246
+    }
+    const bool top_pending = early_top && dt_in > 0.0; // the last chunk is still to be enqueued
+
+    // ---- fill, advance, device -> host
+    auto advance = [&](int m) -> int {
+      const int ja = first_row(m), jb = last_row(m);
+      E2D_CUDA(launch_fused_step(p, g, h->U, h->U2, dt, nullptr, h->d_bits, nullptr, st, nullptr, nullptr, ja, jb));
+      E2D_CUDA(launch_bc_x_rows(p, g, h->U2, faces, ja, jb, st)); // ghost columns of the result
+      E2D_CUDA(cudaEventRecord(ev_cmp[m], st));
+      E2D_CUDA(cudaStreamWaitEvent(h->s_out, ev_cmp[m], 0));
+      E2D_CUDA(copy_rows(U_host_out, h->U2, ja, jb, cudaMemcpyDeviceToHost, h->s_out));
+      return E2D_OK;
+    };
+    for (int k = 0; k < nchunk; ++k)
+    {
+      E2D_CUDA(cudaStreamWaitEvent(st, ev_in[k], 0));
+      const int jlo = k == 0 ? 0 : first_row(k), jhi = k == nchunk - 1 ? jsize : last_row(k);
+      E2D_CUDA(launch_bc_x_rows(p, g, h->U, faces, jlo, jhi, st));
+      if (k == 0)
+      {
+        if (early_top)
+          E2D_CUDA(launch_bc_x_rows(p, g, h->U, faces, jsize - 4, jsize - 2, st));
+        if (faces & E2D_FACES_YMIN)
+          E2D_CUDA(launch_make_boundaries(p, g, h->U, E2D_FACES_YMIN, nullptr, st));
+        E2D_CUDA(cudaEventRecord(ev_ymin, st));
+        if (top_pending)
+        {
+          // now the last chunk may overwrite the two rows the YMIN fill has read
+          const int kl = nchunk - 1;
+          E2D_CUDA(cudaStreamWaitEvent(h->s_in, ev_ymin, 0));
+          E2D_CUDA(copy_rows(h->U, U_host_in, first_row(kl), jsize, cudaMemcpyHostToDevice, h->s_in));
+          E2D_CUDA(cudaEventRecord(ev_in[kl], h->s_in));
+        }
+      }
+      if (k == nchunk - 1 && (faces & E2D_FACES_YMAX))
+        E2D_CUDA(launch_make_boundaries(p, g, h->U, E2D_FACES_YMAX, nullptr, st));
+      if (k >= 1)
+        if (int rc = advance(k - 1))
+          return rc;
+      if (k == nchunk - 1)
+        if (int rc = advance(k))
+          return rc;
+    }
+    // y-ghost rows of the result (faces this slab owns), the CFL reduction of the new state
+    if (faces & (E2D_FACES_YMIN | E2D_FACES_YMAX))
+      E2D_CUDA(launch_make_boundaries(p, g, h->U2, faces & (E2D_FACES_YMIN | E2D_FACES_YMAX), nullptr, st));
+    E2D_CUDA(cudaEventRecord(ev_fin, st));
+    E2D_CUDA(cudaStreamWaitEvent(h->s_out, ev_fin, 0));
+    if (faces & E2D_FACES_YMIN)
+      E2D_CUDA(copy_rows(U_host_out, h->U2, 0, 2, cudaMemcpyDeviceToHost, h->s_out));
+    if (faces & E2D_FACES_YMAX)
+      E2D_CUDA(copy_rows(U_host_out, h->U2, jsize - 2, jsize, cudaMemcpyDeviceToHost, h->s_out));
+    E2D_CUDA(cudaMemcpyAsync(&h->h_loop->invdt_next, h->d_bits, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             h->s_out));
+    E2D_CUDA(cudaStreamSynchronize(h->s_out));
+    E2D_CUDA(cudaStreamSynchronize(st));
+    double inv_next;
+    std::memcpy(&inv_next, &h->h_loop->invdt_next, sizeof inv_next);
+    if (dt_used)
+      *dt_used = dt;
+    if (dt_next)
+      *dt_next = p.cfl / inv_next; // = compute_dt of the state just written (this slab's rows)
     h->loop_primed = false;
     return E2D_OK;
   }

@@ -131,7 +131,11 @@ struct MarchPeers
 // link/peers: nullptr for a single GPU or when the caller exchanges halos itself
 cudaError_t launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
                               const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done,
-                              cudaStream_t st, const MarchPeers * peers = nullptr, FusedLink * link = nullptr);
+                              cudaStream_t st, const MarchPeers * peers = nullptr, FusedLink * link = nullptr,
+                              int j_first = 2, int j_last = 0 /* <= 0: all rows; else rows [j_first, j_last) */);
+// x-ghost columns of rows [jlo, jhi) (faces & E2D_FACES_X)
+cudaError_t launch_bc_x_rows(const e2d_params & p, const Geom & g, double * U, int faces, int jlo, int jhi,
+                             cudaStream_t st);
 // scalar bookkeeping of the device-resident loop
 cudaError_t launch_loop_begin_step(LoopState * st_dev, double cfl, double tEnd, cudaStream_t st);
 cudaError_t launch_loop_end_step(LoopState * st_dev, double tEnd, int max_steps, double * dt_hist, long hist_cap,

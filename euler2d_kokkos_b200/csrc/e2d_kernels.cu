@@ -184,6 +184,17 @@ k_make_boundaries(Geom g, BcArgs a, double * __restrict__ U, const int * __restr
   bc_fill_cell(g, a, U, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+// x-ghost columns of rows [jlo, jhi) only (a.faces = X faces): the host-streamed step fills each chunk of rows as
+// it lands; the y faces follow once their source rows are there (same XMIN, XMAX -> YMIN, YMAX order as
+// HydroRun::make_boundaries, src/HydroRun.h:390-399)
+__global__ void __launch_bounds__(128)
+k_bc_x_rows(Geom g, BcArgs a, double * __restrict__ U, int jlo, int jhi)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < 4 * (jhi - jlo))
+    bc_fill_cell(g, a, U, 4 * g.isize + 4 * jlo + k);
+}
+
 // ------------------------------------------------------------------------------------------
 // CFL reduction: ComputeDtFunctor, src/HydroRunFunctors.h:17-79.
 // max is exact and order independent, so any reduction tree reproduces the reference's value.
@@ -834,6 +845,17 @@ launch_make_boundaries(const e2d_params & p, const Geom & g, double * U, int fac
 }
 
 cudaError_t
+launch_bc_x_rows(const e2d_params & p, const Geom & g, double * U, int faces, int jlo, int jhi, cudaStream_t st)
+{
+  if (jhi <= jlo || !(faces & E2D_FACES_X))
+    return cudaSuccess;
+  const int n = 4 * (jhi - jlo);
+  k_bc_x_rows<<<(n + 127) / 128, 128, 0, st>>>(g, make_bc_args(p, faces & E2D_FACES_X), U, jlo, jhi);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
 launch_reduce_invdt(const e2d_params & p, const Geom & g, const double * U, unsigned long long * d_bits,
                     cudaStream_t st)
 {
@@ -969,7 +991,7 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
 cudaError_t
 launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
                   const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done, cudaStream_t st,
-                  const MarchPeers * peers, FusedLink * link)
+                  const MarchPeers * peers, FusedLink * link, int j_first, int j_last)
 {
   MarchArgs a;
   a.Uin = Uin;
@@ -982,8 +1004,17 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   a.d_dt = d_dt;
   a.invdt_bits = d_invdt_bits;
   const int nbx = (g.nx + (kBX - 4) - 1) / (kBX - 4);
-  a.seg_rows = choose_seg_rows(nbx, g.ny, kMarchMinBlocks);
-  const int  nseg = (g.ny + a.seg_rows - 1) / a.seg_rows;
+  // rows [j_first, j_last) only (host-streamed step); default: the whole slab
+  const int rows = j_last > 0 ? j_last - j_first : g.ny;
+  if (j_last > 0)
+  {
+    if (link || j_first < 2 || j_last > g.jsize - 2 || rows < 1)
+      return cudaErrorInvalidValue;
+    a.j_first = j_first;
+    a.j_last = j_last;
+  }
+  a.seg_rows = choose_seg_rows(nbx, rows, kMarchMinBlocks);
+  const int  nseg = (rows + a.seg_rows - 1) / a.seg_rows;
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
   const int  sol = solver_for(p);
   const bool fuse = d_invdt_bits != nullptr;

@@ -53,6 +53,8 @@ struct MarchArgs
   double *             Uout;
   int                  isize, jsize; // slab extent incl. ghosts
   int                  seg_rows;     // interior rows per block segment
+  int                  j_first = 2;  // rows [j_first, j_last) are produced (j_last <= 0: jsize - 2); a sub-range lets the
+  int                  j_last = 0;   // host-streamed step (e2d_capi.cu) advance chunk by chunk as the rows arrive
   Settings             s;
   StepConsts           c;
   double               dt;         // used when d_dt == nullptr
@@ -171,10 +173,11 @@ struct MarchThread
     ic = i < a.isize ? i : a.isize - 1;
     store = (t >= 2) && (t <= BX - 3) && (i >= 2) && (i <= a.isize - 3);
     plane = (size_t)a.isize * a.jsize;
-    j0 = 2 + seg * a.seg_rows;
+    const int j_end = a.j_last > 0 ? a.j_last : a.jsize - 2;
+    j0 = a.j_first + seg * a.seg_rows;
     j1 = j0 + a.seg_rows;
-    if (j1 > a.jsize - 2)
-      j1 = a.jsize - 2;
+    if (j1 > j_end)
+      j1 = j_end;
     if (j0 >= j1)
       return false;
     const double dt = a.d_dt ? *a.d_dt : a.dt;

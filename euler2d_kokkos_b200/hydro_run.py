@@ -165,6 +165,17 @@ class HydroRun:
         check(lib().e2d_step_host(self._h, in_ptr, out_ptr, C.byref(dt)), "e2d_step_host")
         return dt.value
 
+    def step_host_streamed(self, U_in, U_out, dt: float = 0.0, chunk_rows: int = 0):
+        """The host-resident step with H2D / fused step / D2H overlapped chunk by chunk (e2d_step_host_streamed).
+        `U_in`, `U_out`: numpy arrays or raw host pointers (int).  `dt` > 0: use it (the previous call's dt_next);
+        else dt is computed from the input first.  Returns (dt_used, dt_next)."""
+        pin = U_in if isinstance(U_in, int) else U_in.ctypes.data
+        pout = U_out if isinstance(U_out, int) else U_out.ctypes.data
+        used, nxt = C.c_double(), C.c_double()
+        check(lib().e2d_step_host_streamed(self._h, pin, pout, float(dt), int(chunk_rows), C.byref(used),
+                                           C.byref(nxt)), "e2d_step_host_streamed")
+        return used.value, nxt.value
+
     def device_ptr(self, which: int) -> int:
         return lib().e2d_device_ptr(self._h, int(which)) or 0
 

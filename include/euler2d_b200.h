@@ -262,6 +262,19 @@ int      e2d_get_params(e2d_handle * h, e2d_params * out);
  * copies asynchronous; pageable ones work too. */
 int e2d_step_host(e2d_handle * h, const double * U_host_in, double * U_host_out, double * dt_out);
 
+/* The same step for host-resident state, STREAMED: rows go host -> device in chunks of `chunk_rows` (<= 0: ny/32),
+ * every chunk is advanced as soon as the rows above it have landed and travels back while later chunks are still
+ * arriving — H2D, the fused step and D2H overlap.  That requires dt up front, which is the reference's own call
+ * structure  dt = compute_dt(nStep % 2); godunov_unsplit(nStep, dt)  (src/main.cpp:128,139, src/HydroRun.h:259):
+ *   dt_in > 0   the step uses it (pass the previous call's *dt_next; multi-GPU: the min over the ranks' values);
+ *   dt_in <= 0  dt is computed from the uploaded state first (only the way back then overlaps the compute).
+ * *dt_used receives the dt of this step, *dt_next = cfl / max invDt of the state just written = what compute_dt
+ * returns for it (the reduction rides on the step).  Ghost cells: physical faces are filled on the device (input
+ * and result); on a slab handle the ghost rows at slab interfaces are taken from U_host_in as they are and not
+ * written to U_host_out — the caller exchanges them. */
+int e2d_step_host_streamed(e2d_handle * h, const double * U_host_in, double * U_host_out, double dt_in, int chunk_rows,
+                           double * dt_used, double * dt_next);
+
 /* HydroRun::saveData -> saveVTK (src/HydroRun.h:486-609): ascii .vti, ghosts stripped,
  * <outputDir>/<outputPrefix>_<%07d iStep>.vti, default ostream precision (6 significant digits). */
 int e2d_save_vtk(e2d_handle * h, int which, int iStep);

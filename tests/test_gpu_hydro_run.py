@@ -125,6 +125,52 @@ def test_step_host_round_trip():
     assert_bitwise(out[INNER], ref[INNER], "step_host")
 
 
+@pytest.mark.parametrize("chunk_rows", [0, 16, 23, 1000])
+@pytest.mark.parametrize("bcs", [(1, 1, 1, 1), (2, 2, 2, 2), (3, 3, 3, 3), (3, 3, 2, 1), (1, 2, 3, 3)])
+def test_step_host_streamed_march(bcs, chunk_rows):
+    """A time march whose state lives in host memory, through the streamed step (chunked H2D / step / D2H overlap):
+    every chunking gives the oracle's dt sequence and bits; dt is threaded from call to call (dt_next), the first
+    one is computed from the uploaded state."""
+    hp, op = both_params("four_quadrant", mesh__nx=70, mesh__ny=115, mesh__boundary_type_xmin=bcs[0],
+                         mesh__boundary_type_xmax=bcs[1], mesh__boundary_type_ymin=bcs[2],
+                         mesh__boundary_type_ymax=bcs[3], run__nOutput=-1)
+    nsteps = 12
+    U_ref, dts_ref, n_ref, _ = oracle.run(op, nsteps)
+    a = oracle.init_slab(op)
+    a[:, :2, :] = np.nan  # ghost cells of the host input are never read: the device fills them
+    a[:, -2:, :] = np.nan
+    a[:, :, :2] = np.nan
+    a[:, :, -2:] = np.nan
+    b = np.full_like(a, np.nan)
+    dts, dt = [], 0.0
+    with HydroRun(hp) as hydro:
+        for _ in range(nsteps):
+            used, dt = hydro.step_host_streamed(a, b, dt, chunk_rows)
+            dts.append(used)
+            a, b = b, a
+    assert n_ref == nsteps
+    assert np.array_equal(np.array(dts), dts_ref[1:]), "dt sequence differs from the oracle"
+    assert_bitwise(a[INNER], U_ref[INNER], f"streamed march bc {bcs} chunk {chunk_rows}")
+    # ghost cells of the result = make_boundaries of the new state
+    filled = a.copy()
+    oracle.make_boundaries(op, filled)
+    assert_bitwise(a, filled, "ghost cells of the streamed result")
+
+
+def test_step_host_streamed_equals_step_host():
+    hp, op = both_params("blast", mesh__nx=200, mesh__ny=333)
+    U0 = oracle.init_slab(op)
+    out1, out2 = np.empty_like(U0), np.empty_like(U0)
+    with HydroRun(hp) as hydro:
+        dt1 = hydro.step_host(U0, out1)
+        used, nxt = hydro.step_host_streamed(U0, out2, 0.0, 32)
+        assert used == dt1
+        assert nxt == hydro.step_host(out1, np.empty_like(U0))  # dt_next is compute_dt of the new state
+        used2, _ = hydro.step_host_streamed(U0, out2, dt1, 50)   # dt given by the caller
+        assert used2 == dt1
+    assert_bitwise(out2, out1, "streamed vs plain host step")
+
+
 def test_upload_download_layouts():
     hp, op = both_params("implode", mesh__nx=20, mesh__ny=12)
     rng = np.random.default_rng(3)
