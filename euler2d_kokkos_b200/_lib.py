@@ -44,7 +44,7 @@ class Params(C.Structure):
                                      "postshock_density", "postshock_pressure", "postshock_velocity",
                                      "shock_loc")]
         + [("implementationVersion", C.c_int), ("outputDir", C.c_char * 256), ("outputPrefix", C.c_char * 256),
-           ("honourRiemannSolver", C.c_int)]
+           ("honourRiemannSolver", C.c_int), ("vtkAppended", C.c_int)]
     )
 
     def as_dict(self):
@@ -123,6 +123,11 @@ SIGNATURES = {
     "e2d_step_host": (C.c_int, [_vp, _vp, _vp, _dp]),
     "e2d_step_host_streamed": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, _dp, _dp]),
     "e2d_save_vtk": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "e2d_save_vtk_appended": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "e2d_save_raw": (C.c_int, [_vp, C.c_int, C.c_char_p]),
+    "e2d_compute_radial_profile": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
+    "e2d_save_radial_profile": (C.c_int, [_vp, C.c_int, C.c_char_p]),
+    "e2d_save_npy": (C.c_int, [C.c_char_p, _dp, C.c_long]),
     "e2d_enable_timers": (C.c_int, [_vp, C.c_int]),
     "e2d_get_timers": (C.c_int, [_vp, _dp]),
 }

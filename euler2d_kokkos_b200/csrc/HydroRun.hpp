@@ -152,6 +152,19 @@ private:
   e2d_handle * h_ = nullptr;
 };
 
+// euler2d::ComputeRadialProfileFunctor<device_t> (src/ComputeRadialProfileFunctor.h): apply() bins the density of
+// every cell by its distance from the box centre and writes sedov_blast_radial_distances.npy /
+// sedov_blast_density_profile.npy into the current directory.  The reference passes (params, hydro->U); the array
+// lives behind the HydroRun handle here, so apply takes the run.
+struct ComputeRadialProfileFunctor
+{
+  static void
+  apply(const HydroParams & /*params*/, HydroRun & hydro, DataArray Udata)
+  {
+    check(e2d_save_radial_profile(hydro.handle(), Udata.which, nullptr), "ComputeRadialProfileFunctor::apply");
+  }
+};
+
 } // namespace euler2d_b200
 
 #endif

@@ -3,7 +3,10 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <fstream>
 #include <new>
 #include <sstream>
@@ -105,6 +108,12 @@ struct e2d_handle
   // e2d_step_host_streamed: copy streams and an event pool (created on first use)
   cudaStream_t             s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_pool;
+  // fast output: dense interior blocks, device + pinned double buffers
+  double *    out_dev[2] = { nullptr, nullptr };
+  double *    out_host[2] = { nullptr, nullptr };
+  cudaEvent_t out_ev[2] = { nullptr, nullptr };
+  size_t      out_cap = 0;          // doubles per buffer
+  size_t      out_prefix_bytes = 0; // bytes in front of each variable block in the file
 };
 
 namespace
@@ -626,6 +635,14 @@ extern "C"
     for (auto & e : h->ev_pool)
       if (e)
         cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b)
+    {
+      cudaFree(h->out_dev[b]);
+      if (h->out_host[b])
+        cudaFreeHost(h->out_host[b]);
+      if (h->out_ev[b])
+        cudaEventDestroy(h->out_ev[b]);
+    }
     if (h->s_in)
       cudaStreamDestroy(h->s_in);
     if (h->s_out)
@@ -1332,6 +1349,8 @@ extern "C"
     double * A = h ? array_of(h, which) : nullptr;
     if (!A)
       return fail(E2D_ERR_INVALID, "bad argument");
+    if (h->p.vtkAppended)
+      return e2d_save_vtk_appended(h, which, iStep);
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     const e2d_params &  p = h->p;
     std::vector<double> host(h->n);
@@ -1376,6 +1395,257 @@ extern "C"
     f << "</VTKFile>\n";
     f.close();
     return f.fail() ? fail(E2D_ERR_IO, "write failed: " + filename) : (int)E2D_OK;
+  }
+
+  // ---- fast output: interior gathered on the device, D2H into pinned double buffers overlapped with pwrite ----
+  static int
+  stream_interior_to_file(e2d_handle * h, const double * A, int fd, off_t base, const std::string & fname)
+  {
+    // file layout from `base`: 4 blocks, block v = [prefix bytes] nx*ny doubles of variable v (rows in order)
+    const Geom &   g = h->g;
+    const size_t   nx = (size_t)g.nx, ny = (size_t)g.ny;
+    const size_t   var_bytes = nx * ny * sizeof(double);
+    const off_t    prefix = (off_t)h->out_prefix_bytes;
+    size_t         rows_per_chunk = ((size_t)32 << 20) / (4 * nx * sizeof(double)); // ~32 MB per chunk
+    if (rows_per_chunk < 1)
+      rows_per_chunk = 1;
+    if (rows_per_chunk > ny)
+      rows_per_chunk = ny;
+    const size_t chunk_doubles = 4 * rows_per_chunk * nx;
+    if (h->out_cap < chunk_doubles)
+    {
+      for (int b = 0; b < 2; ++b)
+      {
+        if (h->out_dev[b])
+          cudaFree(h->out_dev[b]);
+        if (h->out_host[b])
+          cudaFreeHost(h->out_host[b]);
+        h->out_dev[b] = nullptr;
+        h->out_host[b] = nullptr;
+      }
+      h->out_cap = 0;
+      for (int b = 0; b < 2; ++b)
+      {
+        E2D_CUDA(cudaMalloc(&h->out_dev[b], chunk_doubles * sizeof(double)));
+        E2D_CUDA(cudaMallocHost(&h->out_host[b], chunk_doubles * sizeof(double)));
+        if (!h->out_ev[b])
+          E2D_CUDA(cudaEventCreateWithFlags(&h->out_ev[b], cudaEventDisableTiming));
+      }
+      h->out_cap = chunk_doubles;
+    }
+    const size_t nchunk = (ny + rows_per_chunk - 1) / rows_per_chunk;
+    auto         issue = [&](size_t k) -> int {
+      const int    b = (int)(k & 1);
+      const size_t r0 = k * rows_per_chunk, nr = std::min(rows_per_chunk, ny - r0);
+      E2D_CUDA(launch_gather_interior(g, A, h->out_dev[b], 2 + (int)r0, (int)nr, h->stream));
+      E2D_CUDA(cudaMemcpyAsync(h->out_host[b], h->out_dev[b], 4 * nr * nx * sizeof(double), cudaMemcpyDeviceToHost,
+                               h->stream));
+      E2D_CUDA(cudaEventRecord(h->out_ev[b], h->stream));
+      return E2D_OK;
+    };
+    if (int rc = issue(0))
+      return rc;
+    for (size_t k = 0; k < nchunk; ++k)
+    {
+      if (k + 1 < nchunk) // the next block travels while this one is written
+        if (int rc = issue(k + 1))
+          return rc;
+      const int    b = (int)(k & 1);
+      const size_t r0 = k * rows_per_chunk, nr = std::min(rows_per_chunk, ny - r0);
+      E2D_CUDA(cudaEventSynchronize(h->out_ev[b]));
+      for (int v = 0; v < 4; ++v)
+      {
+        const char * src = (const char *)(h->out_host[b] + (size_t)v * nr * nx);
+        size_t       left = nr * nx * sizeof(double);
+        off_t        off = base + (off_t)v * (prefix + (off_t)var_bytes) + prefix + (off_t)(r0 * nx * sizeof(double));
+        while (left > 0)
+        {
+          const ssize_t w = pwrite(fd, src, left, off);
+          if (w <= 0)
+            return fail(E2D_ERR_IO, "write failed: " + fname);
+          src += w;
+          off += w;
+          left -= (size_t)w;
+        }
+      }
+    }
+    return E2D_OK;
+  }
+
+  int
+  e2d_save_raw(e2d_handle * h, int which, const char * path)
+  {
+    double * A = h ? array_of(h, which) : nullptr;
+    if (!A || !path)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device);
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0)
+      return fail(E2D_ERR_IO, std::string("cannot open ") + path);
+    h->out_prefix_bytes = 0;
+    const int rc = stream_interior_to_file(h, A, fd, 0, path);
+    return (close(fd) != 0 && rc == E2D_OK) ? fail(E2D_ERR_IO, std::string("close failed: ") + path) : rc;
+  }
+
+  int
+  e2d_save_vtk_appended(e2d_handle * h, int which, int iStep)
+  {
+    double * A = h ? array_of(h, which) : nullptr;
+    if (!A)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device);
+    const e2d_params & p = h->p;
+    const int          nx = p.nx, ny = h->g.ny;
+    std::ostringstream stepNum; // HydroRun.h:537-544
+    stepNum.width(7);
+    stepNum.fill('0');
+    stepNum << iStep;
+    const std::string filename = std::string(p.outputDir) + "/" + p.outputPrefix + "_" + stepNum.str() + ".vti";
+    const unsigned long long var_bytes = (unsigned long long)nx * ny * sizeof(double);
+    std::ostringstream       hd;
+    hd << "<?xml version=\"1.0\"?>\n";
+    hd << "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
+    hd << "  <ImageData WholeExtent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << 0 << "\" "
+       << "Origin=\"" << p.xmin << " " << p.ymin << " " << 0.0 << "\" "
+       << "Spacing=\"" << p.dx << " " << p.dy << " " << 0.0 << "\">\n";
+    hd << "  <Piece Extent=\"" << 0 << " " << nx << " " << 0 << " " << ny << " " << 0 << " " << 0 << " "
+       << "\">\n";
+    hd << "    <PointData>\n    </PointData>\n    <CellData>\n";
+    static const char * varNames[4] = { "rho", "E", "mx", "my" }; // HydroParams.cpp:17
+    for (int v = 0; v < 4; ++v)
+      hd << "    <DataArray type=\"Float64\" Name=\"" << varNames[v] << "\" format=\"appended\" offset=\""
+         << (unsigned long long)v * (8ull + var_bytes) << "\" />\n";
+    hd << "    </CellData>\n  </Piece>\n  </ImageData>\n";
+    hd << "  <AppendedData encoding=\"raw\">\n   _";
+    const std::string head = hd.str();
+    const std::string tail = "\n  </AppendedData>\n</VTKFile>\n";
+
+    const int fd = open(filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0)
+      return fail(E2D_ERR_IO, "cannot open " + filename);
+    int rc = E2D_OK;
+    if (pwrite(fd, head.data(), head.size(), 0) != (ssize_t)head.size())
+      rc = fail(E2D_ERR_IO, "write failed: " + filename);
+    const off_t base = (off_t)head.size();
+    for (int v = 0; v < 4 && rc == E2D_OK; ++v) // each array is preceded by its byte count (UInt64)
+      if (pwrite(fd, &var_bytes, 8, base + (off_t)v * (8 + (off_t)var_bytes)) != 8)
+        rc = fail(E2D_ERR_IO, "write failed: " + filename);
+    if (rc == E2D_OK)
+    {
+      h->out_prefix_bytes = 8;
+      rc = stream_interior_to_file(h, A, fd, base, filename);
+    }
+    if (rc == E2D_OK &&
+        pwrite(fd, tail.data(), tail.size(), base + 4 * (8 + (off_t)var_bytes)) != (ssize_t)tail.size())
+      rc = fail(E2D_ERR_IO, "write failed: " + filename);
+    if (close(fd) != 0 && rc == E2D_OK)
+      rc = fail(E2D_ERR_IO, "close failed: " + filename);
+    return rc;
+  }
+
+  // ---- Sedov post-processing ----
+  int
+  e2d_compute_radial_profile(e2d_handle * h, int which, int nbins, double * distances, double * sums, int * counts)
+  {
+    double * A = h ? array_of(h, which) : nullptr;
+    if (!A)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    cudaSetDevice(h->device);
+    const e2d_params & p = h->p;
+    if (nbins <= 0)
+      nbins = p.blast_nbins;
+    if (nbins <= 0)
+      return fail(E2D_ERR_INVALID, "nbins must be positive");
+    // rows this handle owns: the interior rows, plus the ghost rows of the physical y faces (the reference bins
+    // every cell of the global array, ghost cells included)
+    const bool first = h->whole || h->slab.rank == 0, last = h->whole || h->slab.rank == h->slab.nranks - 1;
+    const int  j_lo = first ? 0 : 2, j_hi = last ? h->g.jsize : h->g.jsize - 2;
+    const RadialArgs a = make_radial_args(p, nbins, j_lo, j_hi);
+    const int        nseg = radial_segments(h->g, nbins, j_hi - j_lo);
+    const size_t     n = (size_t)nbins * nseg * h->g.isize;
+    double *         part_sum = nullptr;
+    int *            part_cnt = nullptr;
+    double *         d_sums = nullptr;
+    int *            d_counts = nullptr;
+    std::vector<double> h_sums(nbins);
+    std::vector<int>    h_counts(nbins);
+    cudaError_t         e = cudaMalloc(&part_sum, n * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&part_cnt, n * sizeof(int));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&d_sums, nbins * sizeof(double));
+    if (e == cudaSuccess)
+      e = cudaMalloc(&d_counts, nbins * sizeof(int));
+    if (e == cudaSuccess)
+      e = launch_radial_profile(h->g, a, A, nseg, part_sum, part_cnt, d_sums, d_counts, h->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(h_sums.data(), d_sums, nbins * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(h_counts.data(), d_counts, nbins * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(h->stream);
+    cudaFree(part_sum);
+    cudaFree(part_cnt);
+    cudaFree(d_sums);
+    cudaFree(d_counts);
+    E2D_CUDA(e);
+    const double dr = a.rmax / nbins; // ComputeRadialProfileFunctor.h:125
+    for (int k = 0; k < nbins; ++k)
+    {
+      if (distances)
+        distances[k] = (k + 0.5) * dr;
+      if (sums)
+        sums[k] = h_sums[k];
+      if (counts)
+        counts[k] = h_counts[k];
+    }
+    return E2D_OK;
+  }
+
+  int
+  e2d_save_npy(const char * path, const double * data, long n)
+  {
+    if (!path || (!data && n > 0) || n < 0)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    // NumPy format 1.0: magic, version, little-endian uint16 header length, dict padded with spaces to a
+    // multiple of 16 bytes and terminated by '\n' (cnpy::create_npy_header)
+    std::string dict = "{'descr': '<f8', 'fortran_order': False, 'shape': (" + std::to_string(n) + ",), }";
+    const size_t unpadded = 10 + dict.size() + 1;
+    dict.append((16 - unpadded % 16) % 16, ' ');
+    dict.push_back('\n');
+    const unsigned short hl = (unsigned short)dict.size();
+    FILE *               f = std::fopen(path, "wb");
+    if (!f)
+      return fail(E2D_ERR_IO, std::string("cannot open ") + path);
+    const unsigned char magic[8] = { 0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0 };
+    bool                ok = std::fwrite(magic, 1, 8, f) == 8;
+    const unsigned char hlb[2] = { (unsigned char)(hl & 0xff), (unsigned char)(hl >> 8) };
+    ok = ok && std::fwrite(hlb, 1, 2, f) == 2;
+    ok = ok && std::fwrite(dict.data(), 1, dict.size(), f) == dict.size();
+    ok = ok && (n == 0 || std::fwrite(data, sizeof(double), (size_t)n, f) == (size_t)n);
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? (int)E2D_OK : fail(E2D_ERR_IO, std::string("write failed: ") + path);
+  }
+
+  int
+  e2d_save_radial_profile(e2d_handle * h, int which, const char * dir)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    if (!h->whole && h->slab.nranks > 1)
+      return fail(E2D_ERR_INVALID, "e2d_save_radial_profile: whole-domain handles only (add the slabs' partial "
+                                   "sums from e2d_compute_radial_profile over the ranks)");
+    const int           nbins = h->p.blast_nbins;
+    std::vector<double> dist(nbins), sums(nbins);
+    std::vector<int>    cnt(nbins);
+    if (int rc = e2d_compute_radial_profile(h, which, nbins, dist.data(), sums.data(), cnt.data()))
+      return rc;
+    for (int k = 0; k < nbins; ++k)
+      sums[k] /= cnt[k]; // ComputeRadialProfileFunctor.h:130 (0/0 = NaN for an empty bin, like the reference)
+    const std::string d = (dir && *dir) ? std::string(dir) + "/" : std::string();
+    if (int rc = e2d_save_npy((d + "sedov_blast_radial_distances.npy").c_str(), dist.data(), nbins)) // :134
+      return rc;
+    return e2d_save_npy((d + "sedov_blast_density_profile.npy").c_str(), sums.data(), nbins); // :135
   }
 
   int

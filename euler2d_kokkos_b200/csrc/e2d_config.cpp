@@ -264,6 +264,7 @@ setup(const Config & cfg, e2d_params * p)
   p->honourRiemannSolver = cfg.boolean("OTHER", "honourRiemannSolver", false) ? 1 : 0;
 
   // [output]
+  p->vtkAppended = cfg.boolean("output", "vtk_appended", false) ? 1 : 0;
   copy_string(p->outputDir, cfg.string("output", "outputDir", "./"));
   copy_string(p->outputPrefix, cfg.string("output", "outputPrefix", "output"));
 

@@ -143,6 +143,22 @@ cudaError_t launch_loop_end_step(LoopState * st_dev, double tEnd, int max_steps,
 cudaError_t launch_eval(const e2d_params & p, int func, const double * d_in, double * d_out, long n,
                         cudaStream_t st);
 
+// ---- post-processing / output (e2d_post.cu) ----
+struct RadialArgs
+{
+  double xmin, ymin, dx, dy, cx, cy, rmax;
+  int    nbins, gw;
+  int    j_lo, j_hi; // local rows [j_lo, j_hi) of the slab are binned
+};
+RadialArgs  make_radial_args(const e2d_params & p, int nbins, int j_lo, int j_hi);
+int         radial_segments(const Geom & g, int nbins, int rows);
+// part_sum / part_cnt: nbins * nseg * isize entries each (scratch); d_sums / d_counts: nbins entries
+cudaError_t launch_radial_profile(const Geom & g, const RadialArgs & a, const double * U, int nseg, double * part_sum,
+                                  int * part_cnt, double * d_sums, int * d_counts, cudaStream_t st);
+// interior cells of rows [j_lo, j_lo + n_rows), ghost columns stripped: out[var][row][nx]
+cudaError_t launch_gather_interior(const Geom & g, const double * U, double * out, int j_lo, int n_rows,
+                                   cudaStream_t st);
+
 int  solver_for(const e2d_params & p); // 2 (HLLC) unless honourRiemannSolver
 void count_launch(int n = 1);
 

@@ -100,6 +100,10 @@ main(int argc, char * argv[])
   hydro->synchronize();
   const double t_tot = secs_since(t0);
 
+  // post-processing for Sedov blast (src/main.cpp:175-179: always hydro->U, whatever the parity of nStep)
+  if (params.problemType == E2D_PROBLEM_BLAST && params.blast_total_energy_inside > 0)
+    euler2d_b200::ComputeRadialProfileFunctor::apply(params, *hydro, hydro->U);
+
   const double t_comp = hydro->godunov_timer.elapsed(), t_prim = hydro->compute_primitive_timer.elapsed();
   const double t_flux = hydro->comp_fluxes_timer.elapsed(), t_update = hydro->update_hydro_timer.elapsed();
   const double t_bound = hydro->boundaries_timer.elapsed();

@@ -10,6 +10,7 @@ All compute happens in libeuler2d_b200.so on the GPU; numpy is only used to hand
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -122,6 +123,28 @@ class HydroRun:
     def saveData(self, Udata: int, iStep: int, name: str = "U") -> None:
         if self.params.ioVTK:
             check(lib().e2d_save_vtk(self._h, int(Udata), int(iStep)), "e2d_save_vtk")
+
+    def save_vtk_appended(self, Udata: int, iStep: int) -> None:
+        """Raw-binary appended .vti (full precision), same name/extents/arrays as saveVTK."""
+        check(lib().e2d_save_vtk_appended(self._h, int(Udata), int(iStep)), "e2d_save_vtk_appended")
+
+    def save_raw(self, Udata: int, path: str) -> None:
+        """Interior cells as raw doubles [var][j][i]."""
+        check(lib().e2d_save_raw(self._h, int(Udata), os.fsencode(path)), "e2d_save_raw")
+
+    def radial_profile(self, Udata: int = E2D_U, nbins: int = 0):
+        """ComputeRadialProfileFunctor: returns (distances, sums, counts); the saved profile is sums / counts."""
+        n = int(nbins) if nbins > 0 else int(self.params.blast_nbins)
+        dist, sums, counts = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        check(lib().e2d_compute_radial_profile(self._h, int(Udata), n, dist.ctypes.data_as(dp),
+                                               sums.ctypes.data_as(dp), counts.ctypes.data_as(C.POINTER(C.c_int))),
+              "e2d_compute_radial_profile")
+        return dist, sums, counts
+
+    def save_radial_profile(self, Udata: int = E2D_U, directory: str = "") -> None:
+        """ComputeRadialProfileFunctor::apply incl. its two .npy files (main.cpp:175-179 passes U)."""
+        check(lib().e2d_save_radial_profile(self._h, int(Udata), os.fsencode(directory)), "e2d_save_radial_profile")
 
     # -- device-resident loop -------------------------------------------------------------------
     def run(self, max_steps: int = -1) -> RunStats:

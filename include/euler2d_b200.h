@@ -74,6 +74,10 @@ typedef struct e2d_params
   /* extension (not in the reference, where `riemann=` is parsed but never used — SURVEY.md §0.4):
    * 0 = reference behaviour (every kernel solves HLLC), 1 = honour riemannSolverType. */
   int    honourRiemannSolver;
+  /* extension: `[output] vtk_appended=yes` makes saveData write the .vti with raw appended binary data (full
+   * precision, interior gathered on the device, D2H overlapped with the file writes) instead of the reference's
+   * 6-digit ascii; 0 = reference behaviour. */
+  int    vtkAppended;
 } e2d_params;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -278,6 +282,31 @@ int e2d_step_host_streamed(e2d_handle * h, const double * U_host_in, double * U_
 /* HydroRun::saveData -> saveVTK (src/HydroRun.h:486-609): ascii .vti, ghosts stripped,
  * <outputDir>/<outputPrefix>_<%07d iStep>.vti, default ostream precision (6 significant digits). */
 int e2d_save_vtk(e2d_handle * h, int which, int iStep);
+
+/* Fast output — same file name, names (rho, E, mx, my: src/HydroParams.cpp:17), extents,
+ * origin/spacing and cell order (ghosts stripped, i fastest) as HydroRun::saveVTK (src/HydroRun.h:507-609), but
+ * the four arrays are Float64 `format="appended"` raw binary (header_type UInt64): bit-exact values instead of 6
+ * significant digits.  The interior is gathered on the device into dense row blocks which travel D2H into pinned
+ * double buffers while the previous block is being written to the file.  e2d_save_vtk dispatches here when
+ * params.vtkAppended is set. */
+int e2d_save_vtk_appended(e2d_handle * h, int which, int iStep);
+/* raw snapshot of the interior: nx*ny doubles per variable, [var][j][i], no header (same pipeline) */
+int e2d_save_raw(e2d_handle * h, int which, const char * path);
+
+/* Sedov post-processing — replaces ComputeRadialProfileFunctor::apply (src/ComputeRadialProfileFunctor.h:86-140,
+ * called by src/main.cpp:175-179 with hydro->U).  Every cell of the array `which` incl. ghost cells is binned by
+ * the distance of its centre from the box centre; nbins <= 0: params.blast_nbins.  Outputs (host, nbins entries
+ * each, any may be NULL): distances[k] = (k + 0.5) * max_radial_distance / nbins, sums[k] = sum of rho,
+ * counts[k] = number of cells; the profile the reference saves is sums[k] / counts[k].  Deterministic (no
+ * atomics); samples the reference bins out of bounds (corner ghost cells) are dropped.  On a slab handle the
+ * sums / counts cover the rows this rank owns (interior rows + the ghost rows of the physical y faces): add them
+ * over the ranks. */
+int e2d_compute_radial_profile(e2d_handle * h, int which, int nbins, double * distances, double * sums, int * counts);
+/* apply() including its output: <dir>/sedov_blast_radial_distances.npy and <dir>/sedov_blast_density_profile.npy
+ * (cnpy::npy_save, src/cnpy/cnpy_io.h:36-63); dir NULL or "": the current directory, like the reference. */
+int e2d_save_radial_profile(e2d_handle * h, int which, const char * dir);
+/* a 1-D float64 array as NumPy .npy version 1.0 (what cnpy::npy_save writes for a rank-1 double view) */
+int e2d_save_npy(const char * path, const double * data, long n);
 
 /* the five public timers of HydroRun (src/HydroRun.h:74-75), seconds accumulated by the
  * e2d_godunov_unsplit path when timing is enabled: [boundaries, godunov, primitive, fluxes, update] */

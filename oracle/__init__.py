@@ -91,6 +91,8 @@ def lib():
         L.e2do_compute_and_store_fluxes_slab.argtypes = [pp, dp, dp, dp, C.c_double, C.c_double, C.c_int]
         L.e2do_update_slab.argtypes = [pp, dp, dp, dp, C.c_int]
         L.e2do_godunov_slab.argtypes = [pp, dp, dp, dp, C.c_double, C.c_int]
+        L.e2do_radial_profile_slab.argtypes = [pp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp,
+                                               C.POINTER(C.c_int)]
         L.e2do_run.argtypes = [pp, dp, dp, C.c_long, dp, C.c_long, dp]
         L.e2do_run.restype = C.c_int
         _lib = L
@@ -212,6 +214,18 @@ def godunov(p: Params, Uin: np.ndarray, dt: float) -> np.ndarray:
     return Uout
 
 
+def radial_profile(p: Params, U: np.ndarray, nbins: int | None = None, j_off: int = 0, j_lo: int = 0,
+                   j_hi: int | None = None):
+    """ComputeRadialProfileFunctor (src/ComputeRadialProfileFunctor.h). Returns (distances, sums, counts); the
+    profile the reference saves is sums / counts."""
+    nbins = p.blast_nbins if nbins is None else nbins
+    j_hi = U.shape[1] if j_hi is None else j_hi
+    dist, sums, counts = np.zeros(nbins), np.zeros(nbins), np.zeros(nbins, dtype=np.int32)
+    lib().e2do_radial_profile_slab(C.byref(p), _dp(U), U.shape[1], j_off, j_lo, j_hi, nbins, _dp(dist), _dp(sums),
+                                   counts.ctypes.data_as(C.POINTER(C.c_int)))
+    return dist, sums, counts
+
+
 def run(p: Params, max_steps: int = -1):
     """Whole-domain driver (main.cpp:86-143). Returns (U_final, dt_seq, nstep, t)."""
     U = alloc(p)
@@ -244,8 +258,8 @@ def _omp_env(threads: int | None):
 
 
 def ref_run(ini: str, nstep: int | None = None, dump: bool = True, threads: int | None = None,
-            states_every: int = 0, binary: str | None = None):
-    """Run the compiled reference on an .ini. Returns dict(meta, U, dts[, states])."""
+            states_every: int = 0, binary: str | None = None, radial: bool = False):
+    """Run the compiled reference on an .ini. Returns dict(meta, U, dts[, states][, radial_*])."""
     exe = binary or ref_binary()
     with tempfile.TemporaryDirectory() as td:
         cmd = [exe, ini]
@@ -256,9 +270,17 @@ def ref_run(ini: str, nstep: int | None = None, dump: bool = True, threads: int 
             cmd += ["--nstep", str(nstep)]
         if states_every:
             cmd += ["--states", str(states_every)]
-        out = subprocess.run(cmd, check=True, capture_output=True, text=True, env=_omp_env(threads)).stdout
+        if radial:
+            cmd += ["--radial"]  # the reference writes its two .npy files into the cwd
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True, env=_omp_env(threads), cwd=td).stdout
         meta = json.loads(out.strip().splitlines()[-1])
         res = {"meta": meta}
+        if radial:
+            res["radial_distances"] = np.load(os.path.join(td, "sedov_blast_radial_distances.npy"))
+            res["radial_profile"] = np.load(os.path.join(td, "sedov_blast_density_profile.npy"))
+            if dump:
+                res["radial_U"] = np.fromfile(prefix + ".Uradial.bin", dtype=np.float64).reshape(
+                    (4, meta["jsize"], meta["isize"]))
         if dump:
             shape = (4, meta["jsize"], meta["isize"])
             res["U"] = np.fromfile(prefix + ".U.bin", dtype=np.float64).reshape(shape)

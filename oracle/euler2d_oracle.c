@@ -652,6 +652,38 @@ load4(const double * A, int isize, int jsize, int i, int j, double s[4])
     s[v] = AT(A, i, j, v);
 }
 
+/* ComputeRadialProfileFunctor::apply + operator(), src/ComputeRadialProfileFunctor.h:86-167 */
+void
+e2do_radial_profile_slab(const e2do_params * p, const double * U, int jsize, int j_off, int j_lo, int j_hi, int nbins,
+                         double * distances, double * sums, int * counts)
+{
+  const int    isize = p->isize, gw = p->ghostWidth;
+  const double xmin = p->xmin, ymin = p->ymin, dx = p->dx, dy = p->dy;
+  const double cx = (p->xmin + p->xmax) / 2, cy = (p->ymin + p->ymax) / 2; /* :95-96 */
+  const double Dx = (p->xmax - p->xmin) / 2, Dy = (p->ymax - p->ymin) / 2; /* :99-100 */
+  const double rmax = sqrt(Dx * Dx + Dy * Dy);                             /* :101 */
+  for (int k = 0; k < nbins; ++k)
+  {
+    sums[k] = 0.0;
+    counts[k] = 0;
+  }
+  for (int i = 0; i < isize; ++i)
+    for (int j = j_lo; j < j_hi; ++j)
+    {
+      const double x = xmin + dx / 2 + (i - gw) * dx; /* :148-149 */
+      const double y = ymin + dy / 2 + (j + j_off - gw) * dy;
+      const double distance = sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy)); /* :151-152 */
+      const int    bin = (int)(distance / rmax * nbins);                       /* :155 */
+      if (bin < 0 || bin >= nbins)
+        continue; /* out of bounds in the reference */
+      counts[bin] += 1;
+      sums[bin] += AT(U, i, j, ID);
+    }
+  const double dr = rmax / nbins; /* :125 */
+  for (int k = 0; k < nbins; ++k)
+    distances[k] = (k + 0.5) * dr;
+}
+
 /* Init*Functor, HydroRunFunctors.h:1347-1827; cell centre as :1384-1385 with the GLOBAL row index */
 void
 e2do_init_slab(const e2do_params * p, double * U, int jsize, int j_off)

@@ -80,6 +80,16 @@ void   e2do_update_slab(const e2do_params * p, double * U, const double * Fx, co
 void   e2do_godunov_slab(const e2do_params * p, const double * Uin, double * Uout, double * work, double dt,
                          int jsize_loc);
 
+/* ---- Sedov post-processing: ComputeRadialProfileFunctor (src/ComputeRadialProfileFunctor.h:86-167) ----
+ * Every cell of the array INCLUDING ghost cells (:106) is binned by the distance of its centre from the box centre,
+ * bin = (int)(distance / max_radial_distance * nbins); counts[bin] += 1, sums[bin] += rho.  The reference writes past
+ * the end of its bin arrays for the corner ghost cells (distance > max_radial_distance, no test at :160-165): those
+ * samples are dropped here.  Serial, i outer / j inner (the order of the compiled reference on one thread).
+ * rows [j_lo, j_hi) of the slab only (whole domain: 0, jsize).  distances[k] = (k + 0.5) * max_radial_distance / nbins.
+ * The profile the reference saves is sums[k] / counts[k] (NaN for an empty bin, :130). */
+void e2do_radial_profile_slab(const e2do_params * p, const double * U, int jsize_loc, int j_off, int j_lo, int j_hi,
+                              int nbins, double * distances, double * sums, int * counts);
+
 /* ---- whole-domain driver (src/main.cpp:86-143) ----
  * U, U2: isize*jsize*4 doubles each.  Runs until t >= tEnd or nStep >= max_steps (max_steps < 0: p->nStepmax).
  * dt_seq (may be NULL) receives dt of main.cpp:87 followed by the dt of every step (capacity dt_cap).

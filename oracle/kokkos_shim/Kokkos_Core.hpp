@@ -22,6 +22,8 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <functional>
+#include <type_traits>
 #include <initializer_list>
 #include <iostream>
 #include <limits>
@@ -228,6 +230,142 @@ deep_copy(const V & dst, const V & src)
 {
   if (dst.data() != src.data())
     std::memcpy(dst.data(), src.data(), sizeof(typename V::value_type) * src.size());
+}
+
+// ---------------------------------------------------------------- rank-1 views (ComputeRadialProfileFunctor.h)
+// View<T*, ...>: plain or with MemoryTraits<Atomic> (element access returns a proxy whose += is an OpenMP atomic).
+// The reference's radial-profile functor indexes bins past the end for the corner ghost cells (bin >= nbins is
+// never tested, ComputeRadialProfileFunctor.h:160-165); a real Kokkos allocation happens to absorb that, so this
+// stand-in over-allocates by kRank1Slack elements instead of corrupting the heap.
+enum MemoryTraitsFlags
+{
+  Unmanaged = 0x01,
+  RandomAccess = 0x02,
+  Atomic = 0x04,
+  Restrict = 0x08,
+  Aligned = 0x10
+};
+template <unsigned F>
+struct MemoryTraits
+{
+  static constexpr unsigned flags = F;
+};
+
+template <class AccessSpace, class MemorySpace>
+struct SpaceAccessibility
+{
+  static constexpr bool accessible = true; // everything lives in host memory here
+};
+
+namespace Impl
+{
+template <class T>
+struct AtomicRef
+{
+  T * p;
+  void
+  operator+=(const T & v) const
+  {
+#pragma omp atomic
+    *p += v;
+  }
+  operator T() const { return *p; }
+};
+template <class... Props>
+struct has_atomic_trait : std::false_type
+{};
+template <class P, class... Rest>
+struct has_atomic_trait<P, Rest...> : has_atomic_trait<Rest...>
+{};
+template <unsigned F, class... Rest>
+struct has_atomic_trait<MemoryTraits<F>, Rest...> : std::integral_constant<bool, (F & Atomic) != 0 || has_atomic_trait<Rest...>::value>
+{};
+constexpr std::size_t kRank1Slack = 64;
+} // namespace Impl
+
+template <class T, class... Props>
+class View<T *, Props...>
+{
+public:
+  using value_type = T;
+  using memory_space = HostSpace;
+  static constexpr int  rank = 1;
+  static constexpr bool is_atomic = Impl::has_atomic_trait<Props...>::value;
+
+  View() = default;
+  View(const std::string & label, std::size_t n0)
+    : m_n0(n0)
+    , m_label(label)
+    , m_data(new T[n0 + Impl::kRank1Slack](), std::default_delete<T[]>())
+  {}
+  template <class... P2>
+  View(const View<T *, P2...> & o) // same allocation seen through other traits
+    : m_n0(o.extent(0))
+    , m_label(o.label())
+    , m_data(o.shared())
+  {}
+
+  decltype(auto)
+  operator()(std::size_t i) const
+  {
+    if constexpr (is_atomic)
+      return Impl::AtomicRef<T>{ m_data.get() + i };
+    else
+      return (m_data.get()[i]);
+  }
+  std::size_t
+  extent(int r) const
+  {
+    return r == 0 ? m_n0 : 1;
+  }
+  std::size_t
+  size() const
+  {
+    return m_n0;
+  }
+  T *
+  data() const
+  {
+    return m_data.get();
+  }
+  const std::string &
+  label() const
+  {
+    return m_label;
+  }
+  const std::shared_ptr<T> &
+  shared() const
+  {
+    return m_data;
+  }
+
+private:
+  std::size_t        m_n0 = 0;
+  std::string        m_label;
+  std::shared_ptr<T> m_data;
+};
+
+template <class T, class... Props>
+void
+deep_copy(const View<T *, Props...> & dst, const T & value)
+{
+  for (std::size_t i = 0; i < dst.size(); ++i)
+    dst.data()[i] = value;
+}
+template <class T, class... Props>
+void
+deep_copy(const View<T *, Props...> & dst, int value) requires(!std::is_same<T, int>::value)
+{
+  for (std::size_t i = 0; i < dst.size(); ++i)
+    dst.data()[i] = static_cast<T>(value);
+}
+template <class Space, class T, class... Props>
+View<T *, HostSpace>
+create_mirror_view_and_copy(const Space &, const View<T *, Props...> & src)
+{
+  View<T *, HostSpace> m(src.label() + "_mirror", src.extent(0));
+  std::memcpy(m.data(), src.data(), sizeof(T) * src.size());
+  return m;
 }
 
 // ---------------------------------------------------------------- policies

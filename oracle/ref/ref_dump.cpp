@@ -3,7 +3,10 @@
 // dumps the conservative state raw (the reference's VTK writer keeps 6 digits only,
 // SURVEY.md §8c trap 3) and can time the solver loop for the CPU baseline.
 //
-// usage: ref_dump <file.ini> [--out PREFIX] [--nstep N] [--warmup W] [--states K]
+// usage: ref_dump <file.ini> [--out PREFIX] [--nstep N] [--warmup W] [--states K] [--radial]
+//   --radial       after the loop, run the reference's Sedov post-processing exactly as main.cpp:175-179 does
+//                  (ComputeRadialProfileFunctor::apply(params, hydro->U) — always U, whatever the step parity):
+//                  writes sedov_blast_radial_distances.npy / sedov_blast_density_profile.npy into the cwd
 //   --warmup W     the loop timer starts after W steps (bench.py's reference arm)
 //   PREFIX.U.bin   final state, doubles, [var][j][i] (whole array incl. ghost cells)
 //   PREFIX.dt.bin  dt used at every step (doubles, nStep entries) preceded by the dt of main.cpp:87
@@ -23,6 +26,7 @@
 
 #include "HydroParams.h"
 #include "HydroRun.h"
+#include "ComputeRadialProfileFunctor.h"
 #include "real_type.h"
 
 using device = Kokkos::Device<Kokkos::DefaultExecutionSpace, Kokkos::DefaultExecutionSpace::memory_space>;
@@ -63,6 +67,7 @@ main(int argc, char * argv[])
     long        nstep_override = -1;
     int         states_every = 0;
     int         warmup = 0;
+    bool        radial = false;
     for (int a = 2; a < argc; ++a)
     {
       if (!strcmp(argv[a], "--out") && a + 1 < argc)
@@ -73,6 +78,8 @@ main(int argc, char * argv[])
         states_every = atoi(argv[++a]);
       else if (!strcmp(argv[a], "--warmup") && a + 1 < argc)
         warmup = atoi(argv[++a]);
+      else if (!strcmp(argv[a], "--radial"))
+        radial = true;
     }
 
     ConfigMap            configMap(ini);
@@ -112,9 +119,13 @@ main(int argc, char * argv[])
     auto   t1 = std::chrono::steady_clock::now();
     double secs = std::chrono::duration<double>(t1 - t0).count();
 
+    if (radial)
+      euler2d::ComputeRadialProfileFunctor<device>::apply(params, hydro->U); // main.cpp:175-179
     if (!out.empty())
     {
       dump_state(*hydro, nStep % 2 != 0, out + ".U.bin");
+      if (radial) // the array the profile was taken from
+        dump_state(*hydro, false, out + ".Uradial.bin");
       FILE * f = fopen((out + ".dt.bin").c_str(), "wb");
       fwrite(dts.data(), sizeof(real_t), dts.size(), f);
       fclose(f);

@@ -37,12 +37,38 @@ SMALL_CASES = {
 }
 
 
+RADIAL_CASES = {
+    # Sedov post-processing (ComputeRadialProfileFunctor): even and odd step counts — main.cpp:178 always passes
+    # hydro->U, so after an odd number of steps the profile is taken from the older array
+    "sedov_80x64_30": (dict(mesh__nx=80, mesh__ny=64, blast__radius=0.04), 30),
+    "sedov_80x64_41": (dict(mesh__nx=80, mesh__ny=64, blast__radius=0.04, blast__nbins=37), 41),
+}
+
+
+def make_radial():
+    binary = oracle.ref_binary(prefer_kokkos=False)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        for name, (ov, steps) in RADIAL_CASES.items():
+            ini = write_deck(os.path.join(td, name + ".ini"), "sedov_blast_2d", run__nOutput=-1, **ov)
+            r = oracle.ref_run(ini, nstep=steps, binary=binary, radial=True, threads=1)  # 1 thread: serial sums
+            out[name + "__U"] = r["radial_U"]
+            out[name + "__Ufinal"] = r["U"]
+            out[name + "__distances"] = r["radial_distances"]
+            out[name + "__profile"] = r["radial_profile"]
+            print(name, r["meta"]["nstep"], r["radial_profile"][:4])
+    np.savez_compressed(os.path.join(HERE, "radial_profile.npz"), **out)
+
+
 def serial_sum(a):
     return float(np.cumsum(a.ravel())[-1])
 
 
 def main():
     assert oracle.ref_available(), "build oracle/_ref first (make -C oracle ref)"
+    if "--radial-only" in sys.argv:
+        return make_radial()
+    make_radial()
     binary = oracle.ref_binary(prefer_kokkos=False)
     small = {}
     with tempfile.TemporaryDirectory() as td:

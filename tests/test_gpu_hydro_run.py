@@ -380,3 +380,122 @@ def test_slab_run_without_peers_is_refused():
     with HydroRun(hp, slab=Slab(0, 2, 16, 0)) as h:
         with pytest.raises(e2d.E2dError, match="peers"):
             h.run(3)
+
+
+# ---- Sedov post-processing and fast output ----
+def _golden_radial():
+    from golden.make_golden import RADIAL_CASES
+    from util import GOLDEN
+    return RADIAL_CASES, np.load(os.path.join(GOLDEN, "radial_profile.npz"))
+
+
+@pytest.mark.parametrize("name", ["sedov_80x64_30", "sedov_80x64_41"])
+def test_radial_profile_against_reference_npy(name, tmp_path):
+    """The Sedov run + ComputeRadialProfileFunctor against the .npy files the compiled reference wrote: state
+    bit-exact, bin counts and distances exact, density profile to 1e-12 (the reference sums with atomics; ours is
+    a deterministic tree)."""
+    cases, G = _golden_radial()
+    ov, steps = cases[name]
+    hp, op = both_params("sedov_blast_2d", run__nOutput=-1, **ov)
+    with HydroRun(hp) as hydro:
+        st = hydro.run(steps)
+        assert st.nStep == steps
+        U = hydro.download(HydroRun.U)  # main.cpp:178 always hands U to the functor
+        assert_bitwise(U[INNER], G[name + "__U"][INNER], "array the profile is taken from")
+        # ghost cells take part in the profile: give U the reference's ghosts (ours may be fresher, Appendix D)
+        hydro.upload(HydroRun.U, G[name + "__U"])
+        dist, sums, counts = hydro.radial_profile(HydroRun.U)
+        d2, s2, c2 = hydro.radial_profile(HydroRun.U)
+        hydro.save_radial_profile(HydroRun.U, str(tmp_path))
+    o_dist, o_sums, o_counts = oracle.radial_profile(op, G[name + "__U"])
+    assert np.array_equal(counts, o_counts)
+    assert_bitwise(dist, G[name + "__distances"], "distances")
+    assert_bitwise(s2, sums, "deterministic sums")
+    np.testing.assert_allclose(sums, o_sums, rtol=1e-12, atol=0)
+    ref = G[name + "__profile"]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        prof = sums / counts
+    assert np.array_equal(np.isnan(prof), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(prof[ok], ref[ok], rtol=1e-12, atol=0)
+    # the files apply() writes
+    assert_bitwise(np.load(tmp_path / "sedov_blast_radial_distances.npy"), G[name + "__distances"])
+    saved = np.load(tmp_path / "sedov_blast_density_profile.npy")
+    assert saved.dtype == np.float64 and saved.shape == ref.shape
+    np.testing.assert_allclose(saved[ok], ref[ok], rtol=1e-12, atol=0)
+
+
+def test_radial_profile_larger_grid_and_bins():
+    hp, op = both_params("sedov_blast_2d", mesh__nx=300, mesh__ny=170, mesh__ymax=0.6, blast__radius=0.03,
+                         blast__nbins=333, run__nOutput=-1)
+    with HydroRun(hp) as hydro:
+        hydro.run(20)
+        U = hydro.download(HydroRun.U)
+        dist, sums, counts = hydro.radial_profile(HydroRun.U)
+    o_dist, o_sums, o_counts = oracle.radial_profile(op, U)
+    assert np.array_equal(counts, o_counts) and counts.sum() <= op.isize * op.jsize
+    assert_bitwise(dist, o_dist)
+    np.testing.assert_allclose(sums, o_sums, rtol=1e-12, atol=0)
+
+
+def _parse_vti_appended(path):
+    raw = open(path, "rb").read()
+    k = raw.index(b'<AppendedData encoding="raw">')
+    start = raw.index(b"_", k) + 1
+    head = raw[:k].decode()
+    import re
+    arrays = re.findall(r'<DataArray type="Float64" Name="(\w+)" format="appended" offset="(\d+)"', head)
+    out = {}
+    for nm, off in arrays:
+        o = start + int(off)
+        nbytes = int(np.frombuffer(raw[o:o + 8], dtype=np.uint64)[0])
+        out[nm] = np.frombuffer(raw[o + 8:o + 8 + nbytes], dtype=np.float64)
+    return head, out, raw
+
+
+@pytest.mark.parametrize("shape", [(70, 45), (1500, 1100)])
+def test_fast_output_vti_appended_and_raw(shape, tmp_path):
+    """Fast output: same names / extents / cell order as HydroRun::saveVTK, values bit-exact (appended raw binary);
+    several row chunks at the larger size."""
+    nx, ny = shape
+    hp, op = both_params("four_quadrant", mesh__nx=nx, mesh__ny=ny, run__nOutput=-1,
+                         output__outputDir=str(tmp_path), output__outputPrefix="fast", output__vtk_appended="yes")
+    assert hp.vtkAppended == 1
+    with HydroRun(hp) as hydro:
+        hydro.run(3)
+        U = hydro.download(HydroRun.U2)
+        hydro.saveData(HydroRun.U2, 3)  # dispatches to the appended writer
+        hydro.save_raw(HydroRun.U2, str(tmp_path / "snap.raw"))
+    head, arrs, raw = _parse_vti_appended(tmp_path / "fast_0000003.vti")
+    assert f'WholeExtent="0 {nx} 0 {ny} 0 0"' in head and 'header_type="UInt64"' in head
+    assert list(arrs) == ["rho", "E", "mx", "my"]
+    for v, nm in enumerate(arrs):
+        assert_bitwise(arrs[nm].reshape(ny, nx), U[v, 2:-2, 2:-2], nm)
+    assert raw.rstrip().endswith(b"</VTKFile>")
+    snap = np.fromfile(tmp_path / "snap.raw", dtype=np.float64).reshape(4, ny, nx)
+    assert_bitwise(snap, U[INNER], "raw snapshot")
+
+
+def test_driver_executable_matches_reference_report(tmp_path):
+    """The euler2d_b200 driver (csrc/main.cpp = the reference's main.cpp over the C++ HydroRun mirror) on a Sedov
+    deck: same final step count / time as the oracle, output files written (appended .vti at the reference's
+    cadence, the two radial-profile .npy files of main.cpp:175-179)."""
+    import subprocess
+    from euler2d_kokkos_b200.decks import write_deck
+    exe = os.path.join(os.path.dirname(e2d.__file__), "euler2d_b200")
+    if not os.path.exists(exe):
+        pytest.skip("driver executable not built")
+    ov = dict(mesh__nx=64, mesh__ny=48, blast__radius=0.05, run__nStepmax=25, run__nOutput=10,
+              output__outputDir=str(tmp_path), output__vtk_appended="yes")
+    ini = write_deck(str(tmp_path / "sedov.ini"), "sedov_blast_2d", **ov)
+    r = subprocess.run([exe, ini], capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    hp, op = both_params("sedov_blast_2d", **ov)
+    U_ref, _, n_ref, t_ref = oracle.run(op, 25)
+    assert f"final: nStep={n_ref} t={float(t_ref).hex()}" in r.stdout.replace("0x1.", "0x1.")
+    names = sorted(f for f in os.listdir(tmp_path) if f.endswith(".vti"))
+    assert names == [f"sedov_blast_2d_{k:07d}.vti" for k in (0, 10, 20, 25)]
+    _, arrs, _ = _parse_vti_appended(tmp_path / names[-1])
+    assert_bitwise(arrs["rho"].reshape(48, 64), U_ref[0, 2:-2, 2:-2], "rho in the last snapshot")
+    prof = np.load(tmp_path / "sedov_blast_density_profile.npy")
+    assert prof.shape == (op.blast_nbins,)

@@ -15,7 +15,7 @@ import oracle
 from euler2d_kokkos_b200.decks import write_deck
 from util import GOLDEN, assert_bitwise, both_params
 
-from golden.make_golden import SMALL_CASES, serial_sum
+from golden.make_golden import RADIAL_CASES, SMALL_CASES, serial_sum
 
 SMALL = np.load(os.path.join(GOLDEN, "small_cases.npz"))
 KAT = np.load(os.path.join(GOLDEN, "kat.npz"))
@@ -137,3 +137,45 @@ def test_oracle_matches_compiled_reference_live(deck, ov, steps):
     assert n == r["meta"]["nstep"] and t == r["meta"]["t"]
     assert_bitwise(dts, r["dts"], "dts")
     assert_bitwise(U, r["U"], deck)
+
+
+# ---- Sedov post-processing (ComputeRadialProfileFunctor.h), fixtures written by the compiled reference itself
+RADIAL = np.load(os.path.join(GOLDEN, "radial_profile.npz"))
+
+
+@pytest.mark.parametrize("name", list(RADIAL_CASES))
+def test_oracle_radial_profile_matches_reference_npy(name):
+    ov, steps = RADIAL_CASES[name]
+    _, op = both_params("sedov_blast_2d", run__nOutput=-1, **ov)
+    U, _, n, _ = oracle.run(op, steps)
+    assert n == steps
+    assert_bitwise(U, RADIAL[name + "__Ufinal"], "sedov state")
+    # main.cpp:178 hands hydro->U to the functor whatever the parity of nStep
+    dist, sums, counts = oracle.radial_profile(op, RADIAL[name + "__U"])
+    assert len(dist) == op.blast_nbins == len(RADIAL[name + "__profile"])
+    assert_bitwise(dist, RADIAL[name + "__distances"], "radial distances")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        prof = sums / counts  # :130, NaN for an empty bin
+    ref = RADIAL[name + "__profile"]
+    assert np.array_equal(np.isnan(prof), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert_bitwise(prof[ok], ref[ok], "density profile (serial order = the reference on one thread)")
+    # every cell of the array is counted except the corner ghost cells the reference bins out of bounds
+    assert counts.sum() <= op.isize * op.jsize and counts.sum() >= op.nx * op.ny
+
+
+def test_oracle_radial_profile_slab_partition():
+    _, op = both_params("sedov_blast_2d", mesh__nx=40, mesh__ny=33, blast__radius=0.06, run__nOutput=-1)
+    U, _, _, _ = oracle.run(op, 10)
+    d0, s0, c0 = oracle.radial_profile(op, U)
+    # rows split into three pieces, addressed as slabs with a global row offset
+    cuts = [0, 9, 20, op.jsize]
+    c = np.zeros_like(c0)
+    s = np.zeros_like(s0)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        slab = np.ascontiguousarray(U[:, a:b, :])
+        _, sk, ck = oracle.radial_profile(op, slab, j_off=a)
+        c += ck
+        s += sk
+    assert np.array_equal(c, c0)
+    np.testing.assert_allclose(s, s0, rtol=1e-13)

@@ -123,3 +123,49 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "liboracle" not in text and "euler2d_oracle" not in text, f
+
+
+def test_save_npy_is_a_valid_numpy_file(tmp_path):
+    """e2d_save_npy (host only) writes what cnpy::npy_save writes for a rank-1 double view: numpy reads it back
+    bit for bit, and the header is 16-byte aligned."""
+    import ctypes as C
+
+    import numpy as np
+
+    import euler2d_kokkos_b200 as e2d
+
+    for n in (0, 1, 7, 100, 12345):
+        a = np.random.default_rng(n).normal(size=n)
+        path = tmp_path / f"a{n}.npy"
+        rc = e2d.lib().e2d_save_npy(os.fsencode(str(path)), a.ctypes.data_as(C.POINTER(C.c_double)), n)
+        assert rc == 0
+        b = np.load(path)
+        assert b.dtype == np.float64 and b.shape == (n,) and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        raw = open(path, "rb").read()
+        hl = raw[8] + 256 * raw[9]
+        assert raw[:8] == b"\x93NUMPY\x01\x00" and (10 + hl) % 16 == 0 and raw[10 + hl - 1:10 + hl] == b"\n"
+
+
+def test_save_npy_matches_cnpy_bytes(tmp_path):
+    """When the compiled reference is here: its sedov_blast_radial_distances.npy (written by cnpy) and ours are the
+    same bytes."""
+    import ctypes as C
+
+    import numpy as np
+
+    import euler2d_kokkos_b200 as e2d
+    import oracle
+    from euler2d_kokkos_b200.decks import write_deck
+
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    ini = write_deck(str(tmp_path / "s.ini"), "sedov_blast_2d", mesh__nx=40, mesh__ny=40, blast__radius=0.06,
+                     run__nOutput=-1)
+    subprocess.run([oracle.ref_binary(prefer_kokkos=False), ini, "--nstep", "2", "--radial"], check=True,
+                   capture_output=True, cwd=tmp_path, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    ref_bytes = open(tmp_path / "sedov_blast_radial_distances.npy", "rb").read()
+    d = np.load(tmp_path / "sedov_blast_radial_distances.npy")
+    mine = tmp_path / "mine.npy"
+    assert e2d.lib().e2d_save_npy(os.fsencode(str(mine)), d.ctypes.data_as(C.POINTER(C.c_double)), d.size) == 0
+    assert open(mine, "rb").read() == ref_bytes
