@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeuler2d_b200.so")
+# E2D_LIB_PATH: development aid (tools/: A/B runs of differently built libraries); the default is the in-tree build
+LIB_PATH = os.environ.get("E2D_LIB_PATH") or os.path.join(HERE, "libeuler2d_b200.so")
 
 E2D_OK = 0
 E2D_U, E2D_U2, E2D_Q = 0, 1, 2
@@ -44,7 +45,7 @@ class Params(C.Structure):
                                      "postshock_density", "postshock_pressure", "postshock_velocity",
                                      "shock_loc")]
         + [("implementationVersion", C.c_int), ("outputDir", C.c_char * 256), ("outputPrefix", C.c_char * 256),
-           ("honourRiemannSolver", C.c_int), ("vtkAppended", C.c_int)]
+           ("honourRiemannSolver", C.c_int), ("vtkAppended", C.c_int), ("arithmetic", C.c_int)]
     )
 
     def as_dict(self):

@@ -1,0 +1,215 @@
+// "fast" arithmetic for the fused marching kernel: the opt-in `[other] arithmetic=fast`.
+//
+// The strict build (e2d_math.cuh / e2d_lean.cuh, -fmad=false) reproduces the reference's x86 arithmetic bit for bit
+// and is FP64-pipe bound at ~500 FP64 instructions per cell.  north_star's parity bar for the state is
+// a tolerance (relative L1/Linf <= 1e-12 per conserved variable), not bit equality, and SURVEY.md Appendix C measured
+// that FMA contraction alone stays below 5e-13 on every deck.  This header spends that tolerance where it buys
+// instructions — the same formulas of src/HydroBaseFunctor.h, evaluated with
+//   * fused multiply-adds, written out explicitly (the library is compiled with -fmad=false, so nothing else changes);
+//   * a/d as a * (1/d) with a Newton-refined reciprocal (error <= ~1 ulp; 1 FP64 instruction per quotient instead of 3,
+//     no fast-path guards and no IEEE slow path: denominators are densities >= smallr and wave-speed differences,
+//     far from the subnormal range the strict build still handles), sqrt likewise without the final correction;
+//   * the minmod limiter on the raw differences (the sign test (dlft*drgt <= 0) as a sign-bit xor, one product with
+//     slope_type after the selection);
+//   * the conservative update as fma chains on the unscaled fluxes.
+// ~300 FP64 instructions per cell.  Every function cites the reference formula it evaluates; tests/test_gpu_fast.py
+// holds the tolerance (<= 1e-12 against the compiled reference after N steps, identical step count).
+//
+// Host-compilable like the other math headers (tests/host_emulation); on the host the reciprocal is 1.0/d.
+#ifndef E2D_FAST_CUH
+#define E2D_FAST_CUH
+
+#include "e2d_lean.cuh"
+
+namespace e2d
+{
+namespace fast
+{
+
+E2D_HD double
+fmadd(double a, double b, double c)
+{
+#if E2D_LEAN_DEVICE
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+
+// 1/d to ~1 ulp: MUFU.RCP64H seed (relative error e0 ~ 2^-20), one cubic step y(1 + e + e^2) -> e0^3, then rounding
+E2D_HD double
+rcp(double d)
+{
+#if E2D_LEAN_DEVICE
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = __fma_rn(-d, y, 1.0);
+  e = __fma_rn(e, e, e);
+  return __fma_rn(y, e, y);
+#else
+  return 1.0 / d;
+#endif
+}
+
+// sqrt(x), x > 0 normal: MUFU.RSQ64H seed, one cubic step on 1/sqrt, one product
+E2D_HD double
+sqrt_pos(double x)
+{
+#if E2D_LEAN_DEVICE
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double g = __dmul_rn(y0, y0);
+  const double e = __fma_rn(x, -g, 1.0);
+  const double p = __fma_rn(e, 0.375, 0.5);
+  const double h = __dmul_rn(y0, e);
+  const double y1 = __fma_rn(p, h, y0);
+  return __dmul_rn(x, y1);
+#else
+  return sqrt(x);
+#endif
+}
+
+// computePrimitives without the sound speed (src/HydroBaseFunctor.h:76-99); ry = 1/d for the trace and the CFL tail.
+// p = (gamma-1)*d*e with e = u_E/d - eken  is evaluated as (gamma-1)*(u_E - d*eken): one rounding less, no division.
+E2D_HD void
+prim(const Settings & s, const StepConsts & c, const double u[4], double q[4], double & ry)
+{
+  const double d = max_nn(u[ID], s.smallr);
+  const double y = rcp(d);
+  const double ux = u[IU] * y;
+  const double uy = u[IV] * y;
+  const double k2 = fmadd(ux, ux, uy * uy); // 2 * eken
+  const double ei = fmadd(-0.5 * d, k2, u[IP]);
+  q[ID] = d;
+  q[IP] = max_nn(c.gm1 * ei, d * s.smallp);
+  q[IU] = ux;
+  q[IV] = uy;
+  ry = y;
+}
+
+// the CFL integrand after the primitive conversion (src/HydroRunFunctors.h:60-72); idx = 1/dx, idy = 1/dy
+E2D_HD double
+cfl_tail(const Settings & s, double idx, double idy, const double q[4], double ry)
+{
+  const double cs = sqrt_pos(s.gamma0 * q[IP] * ry);
+  const double vx = cs + fabs(q[IU]);
+  const double vy = cs + fabs(q[IV]);
+  return fmadd(vx, idx, vy * idy);
+}
+
+// slope_unsplit_hydro_2d_scalar (src/HydroBaseFunctor.h:433-442): dq = minmod(st*a, st*b, dcen), a = q - qMinus,
+// b = qPlus - q.  (dlft*drgt <= 0) <=> a, b differ in sign or one is zero; a zero a or b is selected as the operand
+// of least magnitude by itself, so only the sign test remains.  When a and b agree in sign, dcen has that sign too
+// (or is zero), so the selected operand already carries the result's sign.
+E2D_HD double
+slope(double slope_type, double q, double qPlus, double qMinus)
+{
+  const double a = q - qMinus;
+  const double b = qPlus - q;
+  const double dcen = 0.5 * (qPlus - qMinus);
+  const double sel = slope_type * ((fabs(b) < fabs(a)) ? b : a);
+  const double m = (fabs(dcen) < fabs(sel)) ? dcen : sel;
+#if E2D_LEAN_DEVICE
+  const bool flat = (__double2hiint(a) ^ __double2hiint(b)) < 0;
+#else
+  const bool flat = signbit(a) != signbit(b);
+#endif
+  return flat ? 0.0 : m;
+}
+
+E2D_HD void
+slopes(double slope_type, bool limited, const double q[4], const double qPlus[4], const double qMinus[4], double dq[4])
+{
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    dq[v] = limited ? slope(slope_type, q[v], qPlus[v], qMinus[v]) : 0.0;
+}
+
+// trace_unsplit_2d_along_dir (src/HydroBaseFunctor.h:245-289), all four faces of one cell.  n0 = -s0 (the source
+// terms with the sign pulled out); face = q -+ dq/2 + s0*dtdir/2, evaluated as fma(+-0.5, dq, fma(-n0, dtdir/2, q)).
+E2D_HD void
+trace(const Settings & s, const double q[4], double ry, const double dqX[4], const double dqY[4], double hdtdx,
+      double hdtdy, double xmin[4], double xmax[4], double ymin[4], double ymax[4])
+{
+  const double r = q[ID], p = q[IP], u = q[IU], v = q[IV];
+  const double dv = dqX[IU] + dqY[IV];
+  double       n0[4];
+  n0[ID] = fmadd(u, dqX[ID], fmadd(v, dqY[ID], dv * r));
+  n0[IP] = fmadd(u, dqX[IP], fmadd(v, dqY[IP], dv * (s.gamma0 * p)));
+  n0[IU] = fmadd(u, dqX[IU], fmadd(v, dqY[IU], dqX[IP] * ry));
+  n0[IV] = fmadd(u, dqX[IV], fmadd(v, dqY[IV], dqY[IP] * ry));
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    const double cx = fmadd(-n0[k], hdtdx, q[k]);
+    const double cy = fmadd(-n0[k], hdtdy, q[k]);
+    xmin[k] = fmadd(-0.5, dqX[k], cx);
+    xmax[k] = fmadd(0.5, dqX[k], cx);
+    ymin[k] = fmadd(-0.5, dqY[k], cy);
+    ymax[k] = fmadd(0.5, dqY[k], cy);
+  }
+  xmin[ID] = max_nn(s.smallr, xmin[ID]);
+  xmax[ID] = max_nn(s.smallr, xmax[ID]);
+  ymin[ID] = max_nn(s.smallr, ymin[ID]);
+  ymax[ID] = max_nn(s.smallr, ymax[ID]);
+}
+
+// riemann_hllc (src/HydroBaseFunctor.h:704-809) on (rho, p, un, ut) -> flux (mass, energy, normal, transverse).
+// Same one-sided sampling as hllc_lean (only the star state that can be sampled is evaluated).
+E2D_HD void
+hllc(const Settings & s, const StepConsts & c, double rl_in, double pl_in, double ul, double vl, double rr_in,
+     double pr_in, double ur, double vr, double & f_d, double & f_e, double & f_n, double & f_t)
+{
+  // rl, rr: the inputs are traced face states, already floored at smallr (src/HydroBaseFunctor.h:279-289), so the
+  // reference's fmax(rl, smallr) (:714,:723) is the identity here
+  const double rl = rl_in;
+  const double pl = max_nn(pl_in, rl * s.smallp);
+  const double etotl = fmadd(pl, c.entho, (0.5 * rl) * fmadd(ul, ul, vl * vl));
+  const double rr = rr_in;
+  const double pr = max_nn(pr_in, rr * s.smallp);
+  const double etotr = fmadd(pr, c.entho, (0.5 * rr) * fmadd(ur, ur, vr * vr));
+
+  // fmax(cfastl, cfastr) = sqrt(fmax(gamma * fmax(pl/rl, pr/rr), smallc^2))
+  const double a2 = s.gamma0 * max_nn(pl * rcp(rl), pr * rcp(rr));
+  const double cmax = sqrt_pos(max_nn(a2, c.sc2));
+
+  const double SL = min_nn(ul, ur) - cmax;
+  const double SR = max_nn(ul, ur) + cmax;
+  const double dl = ul - SL;
+  const double dr = SR - ur;
+  const double rcl = rl * dl;
+  const double rcr = rr * dr;
+
+  const double ys = rcp(rcr + rcl);
+  const double ustar = fmadd(rcr, ur, fmadd(rcl, ul, pl - pr)) * ys;
+  const double ptotstar = fmadd(rcr, pl, fmadd(rcl, pr, (rcl * rcr) * (ul - ur))) * ys;
+
+  const bool   sup_l = SL > 0.0;
+  const bool   side_l = sup_l || (ustar > 0.0);
+  const bool   star = !sup_l && (side_l || SR > 0.0);
+  const double Sk = side_l ? SL : SR;
+  const double dk = side_l ? -dl : dr;
+  const double rck = side_l ? -rcl : rcr;
+  const double rk = side_l ? rl : rr;
+  const double ek = side_l ? etotl : etotr;
+  const double pk = side_l ? pl : pr;
+  const double uk = side_l ? ul : ur;
+  const double yk = rcp(Sk - ustar);
+  const double rstar = rck * yk;
+  const double etotstar = fmadd(ptotstar, ustar, fmadd(dk, ek, -(pk * uk))) * yk;
+
+  const double ro = star ? rstar : rk;
+  const double uo = star ? ustar : uk;
+  const double ptoto = star ? ptotstar : pk;
+  const double etoto = star ? etotstar : ek;
+
+  f_d = ro * uo;
+  f_n = fmadd(f_d, uo, ptoto);
+  f_e = (etoto + ptoto) * uo;
+  f_t = f_d * ((f_d > 0.0) ? vl : vr);
+}
+
+} // namespace fast
+} // namespace e2d
+
+#endif // E2D_FAST_CUH

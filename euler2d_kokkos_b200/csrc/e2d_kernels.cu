@@ -18,6 +18,15 @@ namespace
 
 constexpr int kBX = 128;       // threads per block of the marching kernel (= columns incl. 4 halo columns)
 constexpr int kMarchMinBlocks = 3; // blocks of 128 threads per SM (<= 168 registers per thread)
+#ifndef E2D_FAST_MIN_BLOCKS
+#  define E2D_FAST_MIN_BLOCKS 3
+#endif
+constexpr int kMarchMinBlocksFast = E2D_FAST_MIN_BLOCKS; // same for the `arithmetic=fast` instantiations
+constexpr int
+march_min_blocks(int math)
+{
+  return math == 1 ? kMarchMinBlocksFast : kMarchMinBlocks;
+}
 
 __host__ __device__ __forceinline__ size_t
 cell(const Geom & g, int i, int j, int v)
@@ -433,15 +442,15 @@ st_release_sys_u64(unsigned long long * p, unsigned long long v)
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <int SOLVER, bool FUSE_DT, bool LINKED>
-__global__ void __launch_bounds__(kBX, kMarchMinBlocks)
+template <int SOLVER, bool FUSE_DT, bool LINKED, int MATH = 0>
+__global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
 k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
 {
   if (d_done && *d_done)
     return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MarchSmem<kBX> &                  sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
-  MarchThread<kBX, SOLVER, FUSE_DT> th;
+  MarchThread<kBX, SOLVER, FUSE_DT, MATH> th;
   // blockIdx.y -> row segment: with peers the two EDGE segments come first, so that the halo rows are on their way
   // (and usually landed) while the interior is still being computed
   int seg = blockIdx.y;
@@ -715,6 +724,57 @@ k_eval(Settings s, int func, const double * __restrict__ in, double * __restrict
       o[0] = sqrt_pos<true>(a[0], ok);
       o[1] = ok ? 1.0 : 0.0;
       o[2] = sqrt(a[0]);
+      break;
+    }
+    case 12:
+    { // fast_div: (a, d) -> a * fast::rcp(d), a / d
+      const double * a = in + 2 * r;
+      double *       o = out + 2 * r;
+      o[0] = a[0] * fast::rcp(a[1]);
+      o[1] = a[0] / a[1];
+      break;
+    }
+    case 13:
+    { // fast_sqrt: x -> fast::sqrt_pos(x), sqrt(x)
+      const double * a = in + r;
+      double *       o = out + 2 * r;
+      o[0] = fast::sqrt_pos(a[0]);
+      o[1] = sqrt(a[0]);
+      break;
+    }
+    case 14:
+    { // fast_hllc: same record as hllc
+      const double *   a = in + 8 * r;
+      double *         o = out + 4 * r;
+      const StepConsts c = make_step_consts(s);
+      fast::hllc(s, c, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP], o[IU],
+                 o[IV]);
+      break;
+    }
+    case 15:
+    { // fast_cell: u[4] -> q[4], cfl integrand
+      const double *   a = in + 4 * r;
+      double *         o = out + 5 * r;
+      const StepConsts c = make_step_consts(s);
+      double           ry;
+      fast::prim(s, c, a, o, ry);
+      o[4] = fast::cfl_tail(s, 1.0 / s.dx, 1.0 / s.dy, o, ry);
+      break;
+    }
+    case 16:
+    { // fast_slope: same record as slope
+      const double * a = in + 20 * r;
+      double *       o = out + 8 * r;
+      const bool     limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
+      fast::slopes(s.slope_type, limited, a, a + 4, a + 8, o);
+      fast::slopes(s.slope_type, limited, a, a + 12, a + 16, o + 4);
+      break;
+    }
+    case 17:
+    { // fast_trace: same record as trace (q, dqX, dqY, dtdx, dtdy) -> xmin, xmax, ymin, ymax
+      const double * a = in + 14 * r;
+      double *       o = out + 16 * r;
+      fast::trace(s, a, fast::rcp(a[ID]), a + 4, a + 8, 0.5 * a[12], 0.5 * a[13], o, o + 4, o + 8, o + 12);
       break;
     }
     case 5:
@@ -1013,10 +1073,12 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     a.j_first = j_first;
     a.j_last = j_last;
   }
-  a.seg_rows = choose_seg_rows(nbx, rows, kMarchMinBlocks);
+  const int  sol = solver_for(p);
+  // `[other] arithmetic=fast` (e2d_fast.cuh) exists for the HLLC solver, i.e. for everything the reference can run
+  const bool fastm = p.arithmetic == E2D_ARITH_FAST && sol == E2D_RIEMANN_HLLC;
+  a.seg_rows = choose_seg_rows(nbx, rows, march_min_blocks(fastm ? 1 : 0));
   const int  nseg = (rows + a.seg_rows - 1) / a.seg_rows;
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
-  const int  sol = solver_for(p);
   const bool fuse = d_invdt_bits != nullptr;
   FusedLink  lk{};
   if (link)
@@ -1034,7 +1096,7 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     lk = *link;
   }
   const size_t smem = sizeof(MarchSmem<kBX>);
-#define E2D_FS1(SOL, FUSE, LINKED)                                                                        \
+#define E2D_FS1(SOL, FUSE, LINKED, MATH)                                                                     \
   do                                                                                                      \
   {                                                                                                       \
     static bool configured_on[64] = {}; /* per instantiation and device; benign race: idempotent */      \
@@ -1043,30 +1105,32 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     bool & configured = configured_on[dev_ & 63];                                                         \
     if (!configured)                                                                                      \
     {                                                                                                     \
-      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE, LINKED>,                               \
+      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE, LINKED, MATH>,                         \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
       if (e != cudaSuccess)                                                                               \
         return e;                                                                                         \
       configured = true;                                                                                  \
     }                                                                                                     \
-    k_fused_step<SOL, FUSE, LINKED><<<grid, kBX, smem, st>>>(a, d_done, lk);                              \
+    k_fused_step<SOL, FUSE, LINKED, MATH><<<grid, kBX, smem, st>>>(a, d_done, lk);                        \
   } while (0)
-#define E2D_FS(SOL)               \
-  do                              \
-  {                               \
-    if (link)                     \
-      E2D_FS1(SOL, true, true);   \
-    else if (fuse)                \
-      E2D_FS1(SOL, true, false);  \
-    else                          \
-      E2D_FS1(SOL, false, false); \
+#define E2D_FS(SOL, MATH)               \
+  do                                    \
+  {                                     \
+    if (link)                           \
+      E2D_FS1(SOL, true, true, MATH);   \
+    else if (fuse)                      \
+      E2D_FS1(SOL, true, false, MATH);  \
+    else                                \
+      E2D_FS1(SOL, false, false, MATH); \
   } while (0)
   if (sol == 0)
-    E2D_FS(0);
+    E2D_FS(0, 0);
   else if (sol == 1)
-    E2D_FS(1);
+    E2D_FS(1, 0);
+  else if (fastm)
+    E2D_FS(2, 1);
   else
-    E2D_FS(2);
+    E2D_FS(2, 0);
 #undef E2D_FS
 #undef E2D_FS1
   count_launch();
@@ -1089,6 +1153,12 @@ preload_step_kernels()
   E2D_PRE(1)
   E2D_PRE(2)
 #undef E2D_PRE
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_fused_step<2, true, true, 1>);
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_fused_step<2, true, false, 1>);
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_fused_step<2, false, false, 1>);
   return e;
 }
 

@@ -43,6 +43,7 @@
 #define E2D_MARCH_CUH
 
 #include "e2d_lean.cuh"
+#include "e2d_fast.cuh"
 
 namespace e2d
 {
@@ -86,7 +87,11 @@ struct MarchSmem
 #  define E2D_UNROLL
 #endif
 
-template <int BX, int SOLVER, bool FUSE_DT>
+// MATH: 0 = strict (bit-identical to the reference's x86 arithmetic), 1 = fast (e2d_fast.cuh: explicit FMAs and
+// reciprocal-multiply division, within north_star's 1e-12 of the reference; `[other] arithmetic=fast`).  With
+// MATH == 1 the RY ring holds the fast reciprocal of the density, FX / fyP carry UNSCALED fluxes (the update applies
+// dt/dx, dt/dy inside its fma chain) and the solver is the fast HLLC when SOLVER == 2.
+template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0>
 struct MarchThread
 {
   // geometry
@@ -96,7 +101,8 @@ struct MarchThread
   bool   store;     // this thread owns an output column
   size_t plane;     // isize * jsize
   double dtdx, dtdy;
-  Recip  rdx, rdy; // dx, dy and their refined reciprocals (CFL integrand)
+  Recip  rdx, rdy; // dx, dy and their refined reciprocals (CFL integrand); MATH == 1: .y = 1.0 / dx, 1.0 / dy
+  double hdtdx, hdtdy; // MATH == 1: dt/dx/2, dt/dy/2
   int    m3;       // (row being traced) % 3
   // carried across the barrier / rows
   double xmin[4], ymin[4]; // XMIN / YMIN face states of row r (A -> B)
@@ -149,12 +155,17 @@ struct MarchThread
   {
     double q[4];
     Recip  rd;
-    bool   ok = true;
-    prim_lean<true>(a.s, a.c, u, q, rd, ok);
-    if (!ok)
+    if (MATH == 1)
+      fast::prim(a.s, a.c, u, q, rd.y);
+    else
     {
-      Recip unused;
-      prim_lean<false>(a.s, a.c, u, q, unused, ok);
+      bool ok = true;
+      prim_lean<true>(a.s, a.c, u, q, rd, ok);
+      if (!ok)
+      {
+        Recip unused;
+        prim_lean<false>(a.s, a.c, u, q, unused, ok);
+      }
     }
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -186,6 +197,13 @@ struct MarchThread
     bool unused = true;
     rdx = recip_of<true, false>(a.s.dx, unused);
     rdy = recip_of<true, false>(a.s.dy, unused);
+    if (MATH == 1)
+    {
+      rdx.y = 1.0 / a.s.dx;
+      rdy.y = 1.0 / a.s.dy;
+    }
+    hdtdx = 0.5 * dtdx;
+    hdtdy = 0.5 * dtdy;
     invdt = 0.0;
     m3 = (j0 - 1) % 3;
 
@@ -238,17 +256,26 @@ struct MarchThread
 
     // slope_unsplit_hydro_2d (src/HydroBaseFunctor.h:473-516): slope_type outside {1,2} -> zero slopes
     const bool limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
-    slopes_lean(s.slope_type, limited, qC, qE, qW, dqX);
-    slopes_lean(s.slope_type, limited, qC, qN, qS, dqY);
+    if (MATH == 1)
+    {
+      fast::slopes(s.slope_type, limited, qC, qE, qW, dqX);
+      fast::slopes(s.slope_type, limited, qC, qN, qS, dqY);
+      fast::trace(s, qC, rd.y, dqX, dqY, hdtdx, hdtdy, xmin, xmax, ymin, ymax);
+    }
+    else
+    {
+      slopes_lean(s.slope_type, limited, qC, qE, qW, dqX);
+      slopes_lean(s.slope_type, limited, qC, qN, qS, dqY);
 
-    bool ok = true;
-    trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
-    if (!ok)
-      trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
-    trace_face_lean<-1>(s, qC, dqX, s0, dtdx, xmin);
-    trace_face_lean<+1>(s, qC, dqX, s0, dtdx, xmax);
-    trace_face_lean<-1>(s, qC, dqY, s0, dtdy, ymin);
-    trace_face_lean<+1>(s, qC, dqY, s0, dtdy, ymax);
+      bool ok = true;
+      trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
+      if (!ok)
+        trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
+      trace_face_lean<-1>(s, qC, dqX, s0, dtdx, xmin);
+      trace_face_lean<+1>(s, qC, dqX, s0, dtdx, xmax);
+      trace_face_lean<-1>(s, qC, dqY, s0, dtdy, ymin);
+      trace_face_lean<+1>(s, qC, dqY, s0, dtdy, ymax);
+    }
 
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -335,6 +362,40 @@ struct MarchThread
     }
   }
 
+  // MATH == 1: the same phase with the fast arithmetic; fx, fy stay unscaled
+  E2D_HD void
+  compute_B_fast(const MarchArgs & a, const double xl[4], const double yl[4], const double fxE[4], const double uP[4],
+                 double fx[4], double fy[4], double un[4], double qP[4], double & ryP, double & cflv) const
+  {
+    const Settings & s = a.s;
+    if (SOLVER == 2)
+    {
+      fast::hllc(s, a.c, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP], fx[IU],
+                 fx[IV]);
+      fast::hllc(s, a.c, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP], fy[IV],
+                 fy[IU]);
+    }
+    else
+    {
+      riemann<SOLVER>(s, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP], fx[IU],
+                      fx[IV]);
+      riemann<SOLVER>(s, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP], fy[IV],
+                      fy[IU]);
+    }
+    // complete row r-1: U + Fx(i) - Fx(i+1) + Fy(j) - Fy(j+1) (HydroRunFunctors.h:695-713), pend = U + Fx(i)
+    E2D_UNROLL
+    for (int v = 0; v < 4; ++v)
+      un[v] = fast::fmadd(-fy[v], dtdy, fast::fmadd(fyP[v], dtdy, fast::fmadd(-fxE[v], dtdx, pend[v])));
+    cflv = 0.0;
+    if (FUSE_DT)
+    {
+      double qD[4], ryD;
+      fast::prim(s, a.c, unD, qD, ryD);
+      cflv = fast::cfl_tail(s, rdx.y, rdy.y, qD, ryD);
+    }
+    fast::prim(s, a.c, uP, qP, ryP);
+  }
+
   E2D_HD void
   phaseB(const MarchArgs & a, MarchSmem<BX> & sm, int r)
   {
@@ -350,10 +411,15 @@ struct MarchThread
       uC[v] = sm.U[m3][v][t];
       uP[v] = sm.U[sS][v][t];
     }
-    bool ok = true;
-    compute_B<true>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
-    if (!ok)
-      compute_B<false>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
+    if (MATH == 1)
+      compute_B_fast(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv);
+    else
+    {
+      bool ok = true;
+      compute_B<true>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
+      if (!ok)
+        compute_B<false>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
+    }
 
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -378,7 +444,7 @@ struct MarchThread
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      pend[v] = uC[v] + fx[v];
+      pend[v] = (MATH == 1) ? fast::fmadd(fx[v], dtdx, uC[v]) : uC[v] + fx[v];
       fyP[v] = fy[v];
       unD[v] = un[v];
     }
@@ -394,6 +460,13 @@ struct MarchThread
     bool   ok = true;
     double q[4];
     Recip  rd;
+    if (MATH == 1)
+    {
+      fast::prim(a.s, a.c, unD, q, rd.y);
+      if (store)
+        invdt = fmax(invdt, fast::cfl_tail(a.s, rdx.y, rdy.y, q, rd.y));
+      return;
+    }
     prim_lean<true>(a.s, a.c, unD, q, rd, ok);
     double v = cfl_tail_lean<true>(a.s, rdx, rdy, q, rd, ok);
     if (!ok)

@@ -42,6 +42,7 @@ enum { E2D_BC_UNDEFINED = 0, E2D_BC_DIRICHLET = 1, E2D_BC_NEUMANN = 2, E2D_BC_PE
 enum { E2D_PROBLEM_IMPLODE = 0, E2D_PROBLEM_BLAST = 1, E2D_PROBLEM_FOUR_QUADRANT = 2,
        E2D_PROBLEM_DISCONTINUITY = 3, E2D_PROBLEM_SHOCKED_BUBBLE = 4 };
 enum { E2D_RIEMANN_APPROX = 0, E2D_RIEMANN_HLL = 1, E2D_RIEMANN_HLLC = 2 };
+enum { E2D_ARITH_STRICT = 0, E2D_ARITH_FAST = 1 };
 /* bit mask of faces for e2d_k_make_boundaries */
 enum { E2D_FACES_X = 3, E2D_FACES_YMIN = 4, E2D_FACES_YMAX = 8, E2D_FACES_ALL = 15 };
 /* host array layouts for upload / download */
@@ -78,6 +79,13 @@ typedef struct e2d_params
    * precision, interior gathered on the device, D2H overlapped with the file writes) instead of the reference's
    * 6-digit ascii; 0 = reference behaviour. */
   int    vtkAppended;
+  /* extension: `[other] arithmetic=strict|fast`.  0 = strict (default): IEEE double without FMA contraction,
+   * bit-identical to the reference's Kokkos/OpenMP x86 build.  1 = fast: the fused step evaluates the same
+   * formulas with fused multiply-adds and reciprocal-multiply division (csrc/e2d_fast.cuh); results agree with
+   * the reference to north_star's tolerance (relative L1/Linf <= 1e-12 per conserved variable, same step
+   * count), not bit for bit.  Only the fused path (implementationVersion 2 / e2d_run / e2d_step_host*) and the
+   * HLLC solver have a fast form; everything else ignores the switch. */
+  int    arithmetic;
 } e2d_params;
 
 /* ------------------------------------------------------------------------------------------ */

@@ -30,7 +30,7 @@ settings_of(const e2d_params & p)
   return s;
 }
 
-template <int BX, int SOLVER>
+template <int BX, int SOLVER, int MATH = 0>
 static double
 run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_loc, double dt, int seg_rows)
 {
@@ -49,7 +49,7 @@ run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_lo
   const int nbx = (nx + (BX - 4) - 1) / (BX - 4);
   const int nseg = (ny + seg_rows - 1) / seg_rows;
   double    invdt = 0.0;
-  using Thread = MarchThread<BX, SOLVER, true>;
+  using Thread = MarchThread<BX, SOLVER, true, MATH>;
   std::vector<Thread> th(BX);
   MarchSmem<BX> *     sm = new MarchSmem<BX>();
   for (int seg = 0; seg < nseg; ++seg)
@@ -87,6 +87,12 @@ emul_fused_step(const e2d_params * p, const double * Uin, double * Uout, int jsi
 #define CASE(BX, SOL)                                                          \
   if (bx_threads == BX && solver == SOL)                                       \
     inv = run_blocks<BX, SOL>(*p, Uin, Uout, jsize_loc, dt, seg_rows);
+  // `[other] arithmetic=fast`: the same state machine over e2d_fast.cuh (host: fma(), 1.0 / d)
+  if (p->arithmetic == 1 && solver == 2 && bx_threads == 32)
+    inv = run_blocks<32, 2, 1>(*p, Uin, Uout, jsize_loc, dt, seg_rows);
+  else if (p->arithmetic == 1 && solver == 2 && bx_threads == 128)
+    inv = run_blocks<128, 2, 1>(*p, Uin, Uout, jsize_loc, dt, seg_rows);
+  else
   CASE(128, 2)
   CASE(32, 2)
   CASE(16, 2)

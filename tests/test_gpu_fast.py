@@ -1,0 +1,192 @@
+"""`[other] arithmetic=fast` (csrc/e2d_fast.cuh): the fused step with explicit FMAs and reciprocal-multiply division.
+
+It is NOT bit-identical to the reference; its bar is north_star's tolerance — relative L1 / Linf error <= 1e-12 per
+conserved variable after N steps, identical step count (euler2d_kokkos_b200/parity.py states the metric).  The
+reference here is the oracle (pinned bit for bit against the compiled reference, tests/test_oracle_pins.py) at small
+sizes and the strict GPU build (bit-identical to the oracle, tests/test_gpu_hydro_run.py) at large ones.
+"""
+import numpy as np
+import pytest
+
+import euler2d_kokkos_b200 as e2d
+import oracle
+from euler2d_kokkos_b200 import HydroRun
+from euler2d_kokkos_b200.parity import state_deviation
+from util import INNER, assert_bitwise, both_params, gpu_eval, random_state
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # north_star: relative L1 / Linf per conserved variable
+
+
+def ulps(a, b):
+    return np.abs(a - b) / np.spacing(np.abs(b))
+
+
+def run_mode(deck, mode, max_steps=-1, **ov):
+    hp, op = both_params(deck, run__nOutput=-1, other__arithmetic=mode, **ov)
+    with HydroRun(hp) as hydro:
+        st = hydro.run(max_steps)
+        U = hydro.download(HydroRun.U if st.nStep % 2 == 0 else HydroRun.U2)
+        dts = hydro.dt_history()
+    return hp, op, U[INNER], dts, st
+
+
+def assert_within_tolerance(U, U_ref, what):
+    for name, l1, linf in state_deviation(U, U_ref):
+        assert l1 <= TOL and linf <= TOL, f"{what}: {name} rel L1 {l1:.3e} rel Linf {linf:.3e} > {TOL}"
+
+
+def test_params_switch():
+    hp, _ = both_params("implode")
+    assert hp.arithmetic == 0  # strict is the default: the decks of the reference run bit-identically
+    hp, _ = both_params("implode", other__arithmetic="fast")
+    assert hp.arithmetic == 1
+    hp, _ = both_params("implode", other__arithmetic="strict")
+    assert hp.arithmetic == 0
+
+
+def test_fast_division_and_sqrt_within_2_ulp():
+    hp, _ = both_params("implode")
+    rng = np.random.default_rng(5)
+    n = 200000
+    a = rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-30, 30, n)
+    d = rng.uniform(0.5, 1, n) * 10.0 ** rng.uniform(-30, 30, n) * rng.choice([-1.0, 1.0], n)
+    a[::11] = 0.0
+    out = gpu_eval(hp, "fast_div", np.stack([a, d], axis=1))
+    assert np.array_equal(out[:, 1], a / d)
+    assert ulps(out[:, 0], out[:, 1]).max() <= 2.0
+    x = rng.uniform(0.5, 2, n) * 10.0 ** rng.uniform(-60, 60, n)
+    out = gpu_eval(hp, "fast_sqrt", x[:, None])
+    assert np.array_equal(out[:, 1], np.sqrt(x))
+    assert ulps(out[:, 0], out[:, 1]).max() <= 2.0
+
+
+@pytest.mark.parametrize("gamma", [1.4, 1.666])
+def test_fast_functions_against_the_oracle(gamma):
+    hp, op = both_params("implode", hydro__gamma0=gamma)
+    rng = np.random.default_rng(17)
+    n = 50000
+    # HLLC: random face states incl. supersonic ones, identical states, gas at rest
+    rec = np.concatenate([random_state(rng, n), random_state(rng, n)], axis=1)
+    rec[::7, 2] += 8.0
+    rec[::7, 6] += 8.0
+    rec[1::7, 2] -= 8.0
+    rec[1::7, 6] -= 8.0
+    rec[2::7, 4:8] = rec[2::7, 0:4]
+    rec[3::7, 2:4] = 0.0
+    rec[3::7, 6:8] = 0.0
+    rec[3::7, 5] = rec[3::7, 1]
+    ref = oracle.riemann_hllc(op, rec)
+    out = gpu_eval(hp, "fast_hllc", rec)
+    scale = np.abs(ref).max(axis=1, keepdims=True)  # a flux component that cancels is measured against the others
+    assert (np.abs(out - ref) / scale).max() <= 5e-14
+
+    q = random_state(rng, n)
+    u = np.stack([q[:, 0], q[:, 1] / (gamma - 1) + 0.5 * q[:, 0] * (q[:, 2] ** 2 + q[:, 3] ** 2), q[:, 0] * q[:, 2],
+                  q[:, 0] * q[:, 3]], axis=1)
+    u[::5, 2] = 0.0
+    out = gpu_eval(hp, "fast_cell", u)
+    qo, co = oracle.compute_primitives(op, u)
+    inv = (co + np.abs(qo[:, 2])) / op.dx + (co + np.abs(qo[:, 3])) / op.dy
+    np.testing.assert_allclose(out[:, 0], qo[:, 0], rtol=0, atol=0)
+    # p = (gamma-1)(E - kinetic): relative to the total energy it is cut from
+    assert (np.abs(out[:, 1] - qo[:, 1]) / u[:, 1]).max() <= 1e-15
+    assert (np.abs(out[:, 2:4] - qo[:, 2:4]) <= 4 * np.spacing(np.abs(qo[:, 2:4]))).all()
+    np.testing.assert_allclose(out[:, 4], inv, rtol=1e-14)
+
+    # slopes: the same values as the reference's limiter (zeros may differ in sign)
+    st = np.concatenate([random_state(rng, n) for _ in range(5)], axis=1)
+    st[::5, 4:8] = st[::5, 0:4]
+    st[1::5, 4:20] = np.tile(st[1::5, 0:4], 4)
+    dq = oracle.slopes(op, st)
+    out = gpu_eval(hp, "fast_slope", st)
+    assert np.array_equal(out, dq)
+    dts = rng.uniform(0.05, 0.5, (n, 2))
+    ref = oracle.trace(op, np.concatenate([st[:, :4], dq, dts], axis=1))
+    out = gpu_eval(hp, "fast_trace", np.concatenate([st[:, :4], dq, dts], axis=1))
+    scale = np.abs(st[:, :4]).max(axis=1, keepdims=True) + 1.0
+    assert (np.abs(out - ref) / np.tile(scale, (1, 16))).max() <= 5e-15
+
+
+SMALL = {"implode": (96, 48), "blast": (64, 96), "four_quadrant": (80, 80), "discontinuity": (72, 72),
+         "shocked_bubble": (178, 36)}
+
+
+@pytest.mark.parametrize("deck", list(SMALL))
+def test_fast_run_within_1e12_of_the_oracle(deck):
+    nx, ny = SMALL[deck]
+    steps = 200
+    hp, op, U, dts, st = run_mode(deck, "fast", steps, mesh__nx=nx, mesh__ny=ny)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, steps)
+    assert st.nStep == n_ref
+    assert abs(st.t - t_ref) <= TOL * abs(t_ref)
+    np.testing.assert_allclose(dts, dts_ref[1:], rtol=TOL)
+    assert_within_tolerance(U, U_ref[INNER], f"{deck} fast vs oracle")
+
+
+@pytest.mark.parametrize("deck", ["implode", "blast", "four_quadrant", "discontinuity", "shocked_bubble"])
+def test_fast_run_on_stock_decks(deck):
+    """the reference's decks as shipped, 100 steps (the runs SURVEY.md Appendix B pins)"""
+    hp, op, U, dts, st = run_mode(deck, "fast", 100)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 100)
+    assert st.nStep == n_ref == 100
+    np.testing.assert_allclose(dts, dts_ref[1:], rtol=TOL)
+    assert_within_tolerance(U, U_ref[INNER], f"{deck} fast vs oracle")
+
+
+def test_fast_run_until_tend_same_step_count():
+    hp, op, U, dts, st = run_mode("four_quadrant", "fast", mesh__nx=64, mesh__ny=64)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op)
+    assert t_ref == op.tEnd and st.nStep == n_ref and st.t == t_ref
+    assert_within_tolerance(U, U_ref[INNER], "four_quadrant to tEnd")
+
+
+@pytest.mark.parametrize("deck,nx,ny,steps", [("blast", 1024, 1536, 300), ("four_quadrant", 2048, 2048, 200),
+                                              ("implode", 1024, 1024, 300)])
+def test_fast_against_strict_large(deck, nx, ny, steps):
+    """BASELINE-sized grids: the strict GPU build is the reference here (it is bit-identical to the oracle)"""
+    _, _, Uf, dtf, sf = run_mode(deck, "fast", steps, mesh__nx=nx, mesh__ny=ny)
+    _, _, Us, dts, ss = run_mode(deck, "strict", steps, mesh__nx=nx, mesh__ny=ny)
+    assert sf.nStep == ss.nStep == steps
+    np.testing.assert_allclose(dtf, dts, rtol=TOL)
+    assert_within_tolerance(Uf, Us, f"{deck} {nx}x{ny} fast vs strict")
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_unfused_implementations_ignore_the_switch(impl):
+    """implementationVersion 0 / 1 through godunov_unsplit have no fast form: they stay bit-identical"""
+    from test_gpu_hydro_run import host_loop
+
+    hp, op = both_params("implode", mesh__nx=64, mesh__ny=48, other__implementationVersion=impl,
+                         other__arithmetic="fast")
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 20)
+    with HydroRun(hp) as hydro:
+        n, t, dts = host_loop(hydro, hp, 20)
+        U = hydro.download(HydroRun.U if n % 2 == 0 else HydroRun.U2)
+    assert_bitwise(U[INNER], U_ref[INNER], f"impl {impl}")
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_fast_slabs_identical_to_single_domain(nslabs):
+    """the decomposition does not change any cell's arithmetic: N slabs == 1 domain bit for bit in fast mode too"""
+    from test_gpu_hydro_run import run_peer_slabs
+
+    hp, op, U1, dts1, st1 = run_mode("implode", "fast", 60, mesh__nx=96, mesh__ny=50)
+    U, st, dts = run_peer_slabs(hp, nslabs, 60)
+    assert st.nStep == st1.nStep and st.t == st1.t
+    assert_bitwise(dts, dts1, "dt history")
+    assert_bitwise(U, U1, f"fast, {nslabs} slabs")
+
+
+def test_fast_step_host_streamed_matches_device_loop():
+    """the host-buffer entry point honours the switch: same bits as the device-resident loop in fast mode"""
+    hp, op, U1, dts1, st1 = run_mode("four_quadrant", "fast", 6, mesh__nx=96, mesh__ny=80)
+    a = oracle.init_slab(op)
+    b = np.full_like(a, np.nan)
+    dt = 0.0
+    with HydroRun(hp) as hydro:
+        for _ in range(6):
+            used, dt = hydro.step_host_streamed(a, b, dt, 0)
+            a, b = b, a
+    assert_bitwise(a[INNER], U1, "streamed host march, fast")

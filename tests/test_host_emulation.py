@@ -19,7 +19,7 @@ SO = os.path.join(HERE, "host_emulation", "libmarch_emul.so")
 
 @pytest.fixture(scope="module")
 def emul():
-    deps = [SRC] + [os.path.join(HERE, "..", "euler2d_kokkos_b200", "csrc", f) for f in ("e2d_march.cuh", "e2d_math.cuh")]
+    deps = [SRC] + [os.path.join(HERE, "..", "euler2d_kokkos_b200", "csrc", f) for f in ("e2d_march.cuh", "e2d_math.cuh", "e2d_lean.cuh", "e2d_fast.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                "-Wno-unknown-pragmas", "-o", SO, SRC])
@@ -49,6 +49,30 @@ def test_marching_kernel_logic_is_bit_exact(emul, deck, nx, ny, bx, seg):
     out, inv = fused(emul, hp, U, dt, seg, bx)
     assert_bitwise(out[INNER], ref[INNER], f"{deck} {nx}x{ny} bx={bx} seg={seg}")
     assert inv == oracle.compute_invdt(op, ref)
+    mask = np.ones(out.shape, bool)
+    mask[INNER] = False
+    assert np.isnan(out[mask]).all(), "the kernel wrote outside the interior"
+
+
+@pytest.mark.parametrize("deck,nx,ny", [("implode", 70, 41), ("blast", 33, 64), ("shocked_bubble", 130, 9),
+                                        ("four_quadrant", 28, 28)])
+@pytest.mark.parametrize("bx,seg", [(32, 7), (128, 16)])
+def test_fast_arithmetic_marching_logic_and_formulas(emul, deck, nx, ny, bx, seg):
+    """`arithmetic=fast` (e2d_fast.cuh) through the same state machine: the formulas are the reference's up to
+    rounding (1e-13 after one step of a random field; the GPU tests hold the 1e-12 bar over hundreds of steps)."""
+    from euler2d_kokkos_b200.parity import state_deviation
+
+    hp, op = both_params(deck, mesh__nx=nx, mesh__ny=ny, other__arithmetic="fast")
+    assert hp.arithmetic == 1
+    rng = np.random.default_rng(nx * 7 + ny)
+    U = random_conservative_field(rng, op)
+    oracle.make_boundaries(op, U)
+    dt = op.cfl / oracle.compute_invdt(op, U)
+    ref = oracle.godunov(op, U, dt)
+    out, inv = fused(emul, hp, U, dt, seg, bx)
+    for name, l1, linf in state_deviation(out[INNER], ref[INNER]):
+        assert l1 <= 1e-13 and linf <= 1e-13, (name, l1, linf)
+    assert abs(inv - oracle.compute_invdt(op, ref)) <= 1e-13 * inv
     mask = np.ones(out.shape, bool)
     mask[INNER] = False
     assert np.isnan(out[mask]).all(), "the kernel wrote outside the interior"

@@ -96,7 +96,8 @@ def gpu_eval(hp, func, rec):
     import ctypes as C
 
     nout = {"prim": 5, "slope": 8, "trace": 16, "hllc": 4, "approx": 8, "cmpflx": 4, "hll": 4, "hllc_lean": 5,
-            "cell_lean": 6, "trace_lean": 25, "div": 5, "sqrt": 3}[func]
+            "cell_lean": 6, "trace_lean": 25, "div": 5, "sqrt": 3, "fast_div": 2, "fast_sqrt": 2, "fast_hllc": 4,
+            "fast_cell": 5, "fast_slope": 8, "fast_trace": 16}[func]
     rec = np.ascontiguousarray(rec, dtype=np.float64)
     n = rec.shape[0]
     out = np.zeros((n, nout))
