@@ -1232,7 +1232,16 @@ extern "C"
     auto first_row = [&](int k) { return 2 + k * chunk_rows; };
     auto last_row = [&](int k) { return (k == nchunk - 1) ? jsize - 2 : 2 + (k + 1) * chunk_rows; };
     // rows [jlo, jhi) of all four planes
+    // the rows of the four variable planes go as ONE 2-D copy (4 "lines" one plane apart): a quarter of the copy
+    // calls, 52.3 instead of 54.0 ms per 8192^2 step.  E2D_COPY_PER_PLANE=1 restores one copy per plane.
+    static const bool copy2d = std::getenv("E2D_COPY_PER_PLANE") == nullptr;
     auto copy_rows = [&](double * dst, const double * src, int jlo, int jhi, cudaMemcpyKind kind, cudaStream_t s) {
+      if (copy2d)
+      {
+        const size_t o = (size_t)jlo * isize;
+        return cudaMemcpy2DAsync(dst + o, plane * sizeof(double), src + o, plane * sizeof(double),
+                                 (size_t)(jhi - jlo) * isize * sizeof(double), 4, kind, s);
+      }
       for (int v = 0; v < 4; ++v)
       {
         const size_t    o = (size_t)jlo * isize + v * plane;

@@ -69,6 +69,23 @@ sqrt_pos(double x)
 #endif
 }
 
+// 1/sqrt(x), x > 0 normal, to ~1 ulp
+E2D_HD double
+rsqrt_pos(double x)
+{
+#if E2D_LEAN_DEVICE
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double g = __dmul_rn(y0, y0);
+  const double e = __fma_rn(x, -g, 1.0);
+  const double p = __fma_rn(e, 0.375, 0.5);
+  const double h = __dmul_rn(y0, e);
+  return __fma_rn(p, h, y0);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // computePrimitives without the sound speed (src/HydroBaseFunctor.h:76-99); ry = 1/d for the trace and the CFL tail.
 // p = (gamma-1)*d*e with e = u_E/d - eken  is evaluated as (gamma-1)*(u_E - d*eken): one rounding less, no division.
 E2D_HD void
@@ -107,14 +124,16 @@ slope(double slope_type, double q, double qPlus, double qMinus)
   const double a = q - qMinus;
   const double b = qPlus - q;
   const double dcen = 0.5 * (qPlus - qMinus);
-  const double sel = slope_type * ((fabs(b) < fabs(a)) ? b : a);
-  const double m = (fabs(dcen) < fabs(sel)) ? dcen : sel;
 #if E2D_LEAN_DEVICE
-  const bool flat = (__double2hiint(a) ^ __double2hiint(b)) < 0;
+  // flat -> multiply by 0 instead of slope_type (1.0 or 2.0: low word 0, so the choice is one 32-bit select); a zero
+  // `sel` is then the operand of least magnitude and comes out as the (zero) slope
+  const bool   flat = (__double2hiint(a) ^ __double2hiint(b)) < 0;
+  const double st = __hiloint2double(flat ? 0 : __double2hiint(slope_type), 0);
 #else
-  const bool flat = signbit(a) != signbit(b);
+  const double st = (signbit(a) != signbit(b)) ? 0.0 : slope_type;
 #endif
-  return flat ? 0.0 : m;
+  const double sel = st * ((fabs(b) < fabs(a)) ? b : a);
+  return (fabs(dcen) < fabs(sel)) ? dcen : sel;
 }
 
 E2D_HD void
@@ -138,15 +157,23 @@ trace(const Settings & s, const double q[4], double ry, const double dqX[4], con
   n0[IP] = fmadd(u, dqX[IP], fmadd(v, dqY[IP], dv * (s.gamma0 * p)));
   n0[IU] = fmadd(u, dqX[IU], fmadd(v, dqY[IU], dqX[IP] * ry));
   n0[IV] = fmadd(u, dqX[IV], fmadd(v, dqY[IV], dqY[IP] * ry));
+  double cx[4], cy[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    cx[k] = cy[k] = fmadd(-n0[k], hdtdx, q[k]);
+  if (hdtdx != hdtdy) // square cells (every deck of the reference): the half-step predictor is shared by x and y
+  {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      cy[k] = fmadd(-n0[k], hdtdy, q[k]);
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k)
   {
-    const double cx = fmadd(-n0[k], hdtdx, q[k]);
-    const double cy = fmadd(-n0[k], hdtdy, q[k]);
-    xmin[k] = fmadd(-0.5, dqX[k], cx);
-    xmax[k] = fmadd(0.5, dqX[k], cx);
-    ymin[k] = fmadd(-0.5, dqY[k], cy);
-    ymax[k] = fmadd(0.5, dqY[k], cy);
+    xmin[k] = fmadd(-0.5, dqX[k], cx[k]);
+    xmax[k] = fmadd(0.5, dqX[k], cx[k]);
+    ymin[k] = fmadd(-0.5, dqY[k], cy[k]);
+    ymax[k] = fmadd(0.5, dqY[k], cy[k]);
   }
   xmin[ID] = max_nn(s.smallr, xmin[ID]);
   xmax[ID] = max_nn(s.smallr, xmax[ID]);
@@ -164,14 +191,14 @@ hllc(const Settings & s, const StepConsts & c, double rl_in, double pl_in, doubl
   // reference's fmax(rl, smallr) (:714,:723) is the identity here
   const double rl = rl_in;
   const double pl = max_nn(pl_in, rl * s.smallp);
-  const double etotl = fmadd(pl, c.entho, (0.5 * rl) * fmadd(ul, ul, vl * vl));
   const double rr = rr_in;
   const double pr = max_nn(pr_in, rr * s.smallp);
-  const double etotr = fmadd(pr, c.entho, (0.5 * rr) * fmadd(ur, ur, vr * vr));
 
-  // fmax(cfastl, cfastr) = sqrt(fmax(gamma * fmax(pl/rl, pr/rr), smallc^2))
-  const double a2 = s.gamma0 * max_nn(pl * rcp(rl), pr * rcp(rr));
-  const double cmax = sqrt_pos(max_nn(a2, c.sc2));
+  // fmax(cfastl, cfastr) (:732-737) = fmax(sqrt(gamma * fmax(pl/rl, pr/rr)), smallc); the larger ratio is found by
+  // cross-multiplication, and sqrt(gamma p / r) = gamma p / sqrt(gamma p r) costs no reciprocal
+  const bool   big_l = pl * rr > pr * rl;
+  const double gp = s.gamma0 * (big_l ? pl : pr);
+  const double cmax = max_nn(gp * rsqrt_pos(gp * (big_l ? rl : rr)), s.smallc);
 
   const double SL = min_nn(ul, ur) - cmax;
   const double SR = max_nn(ul, ur) + cmax;
@@ -188,20 +215,21 @@ hllc(const Settings & s, const StepConsts & c, double rl_in, double pl_in, doubl
   const bool   side_l = sup_l || (ustar > 0.0);
   const bool   star = !sup_l && (side_l || SR > 0.0);
   const double Sk = side_l ? SL : SR;
-  const double dk = side_l ? -dl : dr;
-  const double rck = side_l ? -rcl : rcr;
   const double rk = side_l ? rl : rr;
-  const double ek = side_l ? etotl : etotr;
   const double pk = side_l ? pl : pr;
   const double uk = side_l ? ul : ur;
-  const double yk = rcp(Sk - ustar);
-  const double rstar = rck * yk;
-  const double etotstar = fmadd(ptotstar, ustar, fmadd(dk, ek, -(pk * uk))) * yk;
-
-  const double ro = star ? rstar : rk;
+  const double vk = side_l ? vl : vr;
+  const double dk = Sk - uk;  // SL - ul = -dl,  SR - ur = dr
+  const double rck = rk * dk; // -rcl, rcr
+  // total energy (:716-721, :725-730) of the side that is sampled only
+  const double ek = fmadd(pk, c.entho, (0.5 * rk) * fmadd(uk, uk, vk * vk));
+  // The star-state formulas (:755-768) with (ustar, ptotstar) replaced by (uk, pk) return the side state itself
+  // (rk dk / dk, ek dk / dk): the supersonic branches of the sampling (:770-797) need no selects of their own.
   const double uo = star ? ustar : uk;
   const double ptoto = star ? ptotstar : pk;
-  const double etoto = star ? etotstar : ek;
+  const double yk = rcp(Sk - uo);
+  const double ro = rck * yk;
+  const double etoto = fmadd(ptoto, uo, fmadd(dk, ek, -(pk * uk))) * yk;
 
   f_d = ro * uo;
   f_n = fmadd(f_d, uo, ptoto);

@@ -19,9 +19,15 @@ namespace
 constexpr int kBX = 128;       // threads per block of the marching kernel (= columns incl. 4 halo columns)
 constexpr int kMarchMinBlocks = 3; // blocks of 128 threads per SM (<= 168 registers per thread)
 #ifndef E2D_FAST_MIN_BLOCKS
-#  define E2D_FAST_MIN_BLOCKS 3
+#  define E2D_FAST_MIN_BLOCKS 4
 #endif
 constexpr int kMarchMinBlocksFast = E2D_FAST_MIN_BLOCKS; // same for the `arithmetic=fast` instantiations
+#ifndef E2D_MARCH_UNROLL
+#  define E2D_MARCH_UNROLL 2
+#endif
+// rows per trip of the marching loop of the fast instantiations (ring slot r & 1 becomes a constant, fewer carried
+// register moves: +2 %; the strict kernel, at 158 registers, loses 4 % to the same unrolling)
+constexpr int kMarchUnrollFast = E2D_MARCH_UNROLL;
 constexpr int
 march_min_blocks(int math)
 {
@@ -463,6 +469,7 @@ k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
   if (active)
   {
     __syncthreads();
+#pragma unroll(MATH == 1 ? kMarchUnrollFast : 1)
     for (int r = th.j0 - 1; r <= th.j1; ++r)
     {
       th.phaseA(a, sm, r);

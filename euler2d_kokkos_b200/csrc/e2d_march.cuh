@@ -70,22 +70,87 @@ struct MarchArgs
   int      peer_lo_jsize = 0, peer_hi_jsize = 0;
 };
 
-template <int BX>
-struct MarchSmem
-{
-  double Q[3][4][BX];
-  double RY[3][BX];
-  double U[3][4][BX];
-  double XMAX[2][4][BX];
-  double YMAX[2][4][BX];
-  double FX[2][4][BX];
-};
-
 #if defined(__CUDACC__)
 #  define E2D_UNROLL _Pragma("unroll")
 #else
 #  define E2D_UNROLL
 #endif
+
+// The four variables of a cell are kept as two 16-byte pairs, (rho, p|E) and (u|mx, v|my), each pair array indexed
+// by the lane: a row of states is read and written with 128-bit shared-memory accesses (2 per state instead of 4;
+// consecutive lanes are 16 bytes apart, so every quarter-warp covers all 32 banks — conflict-free, also for the
+// west / east neighbour's lane).
+struct alignas(16) Pair
+{
+  double a, b;
+};
+
+template <int BX>
+struct MarchSmem
+{
+  Pair   Q[3][2][BX];
+  double RY[3][BX];
+  Pair   U[3][2][BX];
+  Pair   XMAX[2][2][BX];
+  Pair   YMAX[2][2][BX];
+  Pair   FX[2][2][BX];
+};
+
+// PACKED = false: the same storage read as four planes double[4][BX] with 64-bit accesses (the strict kernel, whose
+// register allocation is 3 % better off without the pairing: profiles/r1_fused_step_variants.txt).
+template <bool PACKED, int BX>
+E2D_HD double *
+slot_of(Pair (&row)[2][BX], int v, int t)
+{
+  if (PACKED)
+    return (v & 1) ? &row[v >> 1][t].b : &row[v >> 1][t].a;
+  return reinterpret_cast<double *>(&row[0][0]) + v * BX + t;
+}
+
+template <bool PACKED, int BX>
+E2D_HD void
+ld4(const Pair (&row)[2][BX], int t, double v[4])
+{
+  if (PACKED)
+  {
+    const Pair x = row[0][t], y = row[1][t];
+    v[0] = x.a;
+    v[1] = x.b;
+    v[2] = y.a;
+    v[3] = y.b;
+  }
+  else
+  {
+    const double * r = reinterpret_cast<const double *>(&row[0][0]) + t;
+    E2D_UNROLL
+    for (int k = 0; k < 4; ++k)
+      v[k] = r[k * BX];
+  }
+}
+
+template <bool PACKED, int BX>
+E2D_HD void
+st4(Pair (&row)[2][BX], int t, const double v[4])
+{
+  if (PACKED)
+  {
+    Pair x, y;
+    x.a = v[0];
+    x.b = v[1];
+    y.a = v[2];
+    y.b = v[3];
+    row[0][t] = x;
+    row[1][t] = y;
+  }
+  else
+  {
+    double * r = reinterpret_cast<double *>(&row[0][0]) + t;
+    E2D_UNROLL
+    for (int k = 0; k < 4; ++k)
+      r[k * BX] = v[k];
+  }
+}
+
 
 // MATH: 0 = strict (bit-identical to the reference's x86 arithmetic), 1 = fast (e2d_fast.cuh: explicit FMAs and
 // reciprocal-multiply division, within north_star's 1e-12 of the reference; `[other] arithmetic=fast`).  With
@@ -94,6 +159,7 @@ struct MarchSmem
 template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0>
 struct MarchThread
 {
+  static constexpr bool PACK = (MATH == 1); // shared-memory rows as 16-byte pairs
   // geometry
   int    t, tm, tp; // lane in the block, clamped west / east lanes
   int    i, ic;     // grid column, clamped grid column
@@ -131,13 +197,15 @@ struct MarchThread
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.U[slot][v][t]);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(slot_of<PACK>(sm.U[slot], v, t));
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p + v * plane) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 #else
+    double u[4];
     for (int v = 0; v < 4; ++v)
-      sm.U[slot][v][t] = p[v * plane];
+      u[v] = p[v * plane];
+    st4<PACK>(sm.U[slot], t, u);
 #endif
   }
 
@@ -167,9 +235,7 @@ struct MarchThread
         prim_lean<false>(a.s, a.c, u, q, unused, ok);
       }
     }
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-      sm.Q[slot][v][t] = q[v];
+    st4<PACK>(sm.Q[slot], t, q);
     sm.RY[slot][t] = rd.y;
   }
 
@@ -213,21 +279,19 @@ struct MarchThread
     convert_into(a, sm, u, (j0 - 2) % 3);
     load_row(a, j0 - 1, u);
     convert_into(a, sm, u, (j0 - 1) % 3);
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-      sm.U[(j0 - 1) % 3][v][t] = u[v];
+    st4<PACK>(sm.U[(j0 - 1) % 3], t, u);
     load_row(a, j0, u);
     convert_into(a, sm, u, j0 % 3);
+    st4<PACK>(sm.U[j0 % 3], t, u);
+    st4<PACK>(sm.YMAX[(j0 - 2) & 1], t, u); // any valid state: the south face of row j0-1 is solved but unused
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      sm.U[j0 % 3][v][t] = u[v];
-      sm.YMAX[(j0 - 2) & 1][v][t] = u[v]; // any valid state: the south face of row j0-1 is solved but unused
-      sm.FX[(j0 - 1) & 1][v][t] = 0.0;    // read (and unused) by the first phase B
       fyP[v] = 0.0;
       pend[v] = 0.0;
       unD[v] = u[v]; // any valid state
     }
+    st4<PACK>(sm.FX[(j0 - 1) & 1], t, fyP); // zeros: read (and unused) by the first phase B
     return true;
   }
 
@@ -241,15 +305,11 @@ struct MarchThread
     // row r+2 (clamped: the last fetch of the topmost segment is a harmless repeat) -> U ring slot of row r-1,
     // consumed at the bottom of phase B
     prefetch_row(a, sm, (r + 2 < a.jsize) ? r + 2 : a.jsize - 1, sS);
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-    {
-      qC[v] = sm.Q[sC][v][t];
-      qW[v] = sm.Q[sC][v][tm];
-      qE[v] = sm.Q[sC][v][tp];
-      qS[v] = sm.Q[sS][v][t];
-      qN[v] = sm.Q[sN][v][t];
-    }
+    ld4<PACK>(sm.Q[sC], t, qC);
+    ld4<PACK>(sm.Q[sC], tm, qW);
+    ld4<PACK>(sm.Q[sC], tp, qE);
+    ld4<PACK>(sm.Q[sS], t, qS);
+    ld4<PACK>(sm.Q[sN], t, qN);
     Recip rd;
     rd.d = qC[ID];
     rd.y = sm.RY[sC][t];
@@ -277,12 +337,8 @@ struct MarchThread
       trace_face_lean<+1>(s, qC, dqY, s0, dtdy, ymax);
     }
 
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-    {
-      sm.XMAX[r & 1][v][t] = xmax[v];
-      sm.YMAX[r & 1][v][t] = ymax[v];
-    }
+    st4<PACK>(sm.XMAX[r & 1], t, xmax);
+    st4<PACK>(sm.YMAX[r & 1], t, ymax);
   }
 
   // Everything of phase B that is arithmetic: the x-face and y-face solves, the update of row r-1, and — advanced
@@ -402,15 +458,11 @@ struct MarchThread
     const int sS = (m3 == 0) ? 2 : m3 - 1;
     double    xl[4], yl[4], fxE[4], uC[4], uP[4], fx[4], fy[4], un[4], qP[4], ryP = 0.0, cflv;
     wait_prefetch(); // row r+2, in flight since phase A
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-    {
-      xl[v] = sm.XMAX[r & 1][v][tm];
-      yl[v] = sm.YMAX[(r - 1) & 1][v][t];
-      fxE[v] = sm.FX[r & 1][v][tp];
-      uC[v] = sm.U[m3][v][t];
-      uP[v] = sm.U[sS][v][t];
-    }
+    ld4<PACK>(sm.XMAX[r & 1], tm, xl);
+    ld4<PACK>(sm.YMAX[(r - 1) & 1], t, yl);
+    ld4<PACK>(sm.FX[r & 1], tp, fxE);
+    ld4<PACK>(sm.U[m3], t, uC);
+    ld4<PACK>(sm.U[sS], t, uP);
     if (MATH == 1)
       compute_B_fast(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv);
     else
@@ -421,12 +473,8 @@ struct MarchThread
         compute_B<false>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
     }
 
-    E2D_UNROLL
-    for (int v = 0; v < 4; ++v)
-    {
-      sm.FX[(r + 1) & 1][v][t] = fx[v];
-      sm.Q[sS][v][t] = qP[v]; // row r+2 -> primitive ring, slot of row r-1 (last read in A(r))
-    }
+    st4<PACK>(sm.FX[(r + 1) & 1], t, fx);
+    st4<PACK>(sm.Q[sS], t, qP); // row r+2 -> primitive ring, slot of row r-1 (last read in A(r))
     sm.RY[sS][t] = ryP;
 
     // the CFL integrand just computed belongs to row r-2 (completed by the previous phase B)
