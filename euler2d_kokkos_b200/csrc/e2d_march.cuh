@@ -23,8 +23,9 @@
 // Shared memory (ring slots are row % 3 or row & 1; one barrier per row suffices):
 //   Q[r%3]       primitives of rows r-1, r, r+1      written in B(r-2)   read in A(r-1..r+1)
 //   RY[r%3]      refined 1/rho of the same rows      own column only
-//   U[r%3]       conservatives of rows r, r+1, r+2   own column only     row r+2 lands by cp.async issued in
-//                                                                        A(r), is read in B(r) (-> Q) and B(r+2)
+//   U[r%3]       conservatives of rows r, r+1, r+2   own column only     row r+3 is fetched by cp.async issued in
+//                                                                        B(r) into the slot of row r (just read); it is
+//                                                                        read in B(r+1) (-> Q) and B(r+3)
 //   XMAX[r&1]    XMAX face states of row r           written in A(r)     read in B(r) by the east lane
 //   YMAX[r&1]    YMAX face states of row r           own column only     written A(r), read B(r+1)
 //   FX[(r+1)&1]  x fluxes of row r                   written in B(r)     read in B(r+1) by the west lane
@@ -292,6 +293,8 @@ struct MarchThread
       unD[v] = u[v]; // any valid state
     }
     st4<PACK>(sm.FX[(j0 - 1) & 1], t, fyP); // zeros: read (and unused) by the first phase B
+    // row j0+1, read as "row r+2" by the first phase B (r = j0-1)
+    prefetch_row(a, sm, (j0 + 1 < a.jsize) ? j0 + 1 : a.jsize - 1, (j0 + 1) % 3);
     return true;
   }
 
@@ -302,9 +305,7 @@ struct MarchThread
     const Settings & s = a.s;
     const int        sC = m3, sS = (m3 == 0) ? 2 : m3 - 1, sN = (m3 == 2) ? 0 : m3 + 1;
     double           qC[4], qW[4], qE[4], qS[4], qN[4], dqX[4], dqY[4], s0[4], xmax[4], ymax[4];
-    // row r+2 (clamped: the last fetch of the topmost segment is a harmless repeat) -> U ring slot of row r-1,
-    // consumed at the bottom of phase B
-    prefetch_row(a, sm, (r + 2 < a.jsize) ? r + 2 : a.jsize - 1, sS);
+    (void)r;
     ld4<PACK>(sm.Q[sC], t, qC);
     ld4<PACK>(sm.Q[sC], tm, qW);
     ld4<PACK>(sm.Q[sC], tp, qE);
@@ -463,6 +464,9 @@ struct MarchThread
     ld4<PACK>(sm.FX[r & 1], tp, fxE);
     ld4<PACK>(sm.U[m3], t, uC);
     ld4<PACK>(sm.U[sS], t, uP);
+    // row r+3 (clamped: the last fetches of the topmost segment are harmless repeats) -> the U ring slot of row r,
+    // just read; it is consumed by phase B(r+1), a whole B and A phase from here (own column only: no hazard)
+    prefetch_row(a, sm, (r + 3 < a.jsize) ? r + 3 : a.jsize - 1, m3);
     if (MATH == 1)
       compute_B_fast(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv);
     else

@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(256) k(double * out, int iters, double seed)
 #pragma unroll
       for (int k = 0; k < ALU_PER_FP64; ++k)
         y[c] = (y[c] ^ (y[c] << 1)) + k; // LOP3/SHF/IADD-class work
+      // ALU_PER_FP64 < 0: exactly -ALU_PER_FP64 single ALU instructions (LOP3 with two live operands) per FP64 one
+#pragma unroll
+      for (int k = 0; k < -ALU_PER_FP64; ++k)
+        y[c] = (y[c] ^ it) & (y[(c + 1) % CHAINS] | k);
     }
   }
   double s = 0;
@@ -90,5 +94,10 @@ main()
   run<8, 2, 0>("DFMA + 6 ALU each", 4);
   run<8, 0, 3>("DSETP+select+DADD+DMUL", 4);
   run<4, 1, 0>("DFMA + 3 ALU each", 3);
+  // does an FP64 instruction leave its second dispatch cycle to another pipe?  N DFMA + N (2N) single ALU instructions
+  run<8, -1, 0>("DFMA + 1 LOP3 each", 4);
+  run<8, -2, 0>("DFMA + 2 LOP3 each", 4);
+  run<8, -3, 0>("DFMA + 3 LOP3 each", 4);
+  run<8, -1, 0>("DFMA + 1 LOP3 each", 8);
   return 0;
 }
