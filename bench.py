@@ -38,10 +38,10 @@ METRIC = "Mcell-updates/s (fp64)"
 UNIT = "Mcell-updates/s"
 
 
-def workload_overrides(n_gpus: int, nx=NX_PER_GPU, ny=NY_PER_GPU):
+def workload_overrides(n_gpus: int, nx=NX_PER_GPU, ny=NY_PER_GPU, arithmetic="strict"):
     # keep dx == dy when the domain is stretched in y for weak scaling
     return dict(mesh__nx=nx, mesh__ny=ny * n_gpus, mesh__ymax=float(n_gpus), run__nOutput=-1,
-                run__nStepmax=10 ** 8, run__tEnd=1e9)
+                run__nStepmax=10 ** 8, run__tEnd=1e9, other__arithmetic=arithmetic)
 
 
 def config_dict(n_gpus: int):
@@ -237,16 +237,16 @@ def ours(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     roofline = None
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        pass
     if kernel_seconds > 0:
         per_launch = kernel_seconds / K
         cells_per_launch = NX_PER_GPU * NY_PER_GPU  # one launch = one GPU's slab
         achieved = ALGO_BYTES_PER_CELL * cells_per_launch / per_launch * 1e-9
-        traffic, prof = None, {}
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic = prof.get("k_fused_step_8192x8192")
-        except Exception:
-            pass
+        traffic = prof.get("k_fused_step_8192x8192")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                     "traffic": traffic, "kernel": "k_fused_step<HLLC, fused dt>", "kernel_ms_per_launch": per_launch * 1e3,
                     "kernel_share_of_step": kernel_seconds / seconds, "peak_source": peak_src,
@@ -264,6 +264,64 @@ def ours(args):
                                      "peak_per_clk_per_smsp": peak_rate, "frac": rate / peak_rate, "sm_mhz": mhz,
                                      "source": "ncu instruction count (profiles/) / live CUDA-event time; peak measured "
                                                "by tools/microbench/fp64_peak.cu"}
+
+    # ---------------- the same loop with `[other] arithmetic=fast` (csrc/e2d_fast.cuh): explicit FMAs and
+    # reciprocal-multiply division, inside north_star's 1e-12 of the reference instead of bit-identical to it.
+    # Reported beside the strict headline, with the deviation between the two states measured in this very run.
+    fast = None
+    if not args.no_fast:
+        hpf = e2d.HydroParams.from_string(deck_text("four_quadrant", **workload_overrides(world, arithmetic="fast")))
+        if not distributed:
+            hf = e2d.HydroRun(hpf)
+            hf.enable_timers(True)
+            hf.run(W)
+            barrier()
+            stf = hf.run(W + K)
+            barrier()
+            f_seconds, f_kernel = stf.seconds, stf.seconds_step_kernel
+        else:
+            runf = PeerSlabRun(hpf, device=dev)
+            runf.hydro.enable_timers(True)
+            runf.run(W)
+            barrier()
+            stf = runf.run(W + K)
+            barrier()
+            tmax = torch.tensor([stf.seconds, stf.seconds_step_kernel], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            f_seconds, f_kernel = float(tmax[0].item()), float(tmax[1].item())
+            hf = runf.hydro
+        assert stf.nStep == W + K
+        f_per_launch = f_kernel / K
+        f_achieved = ALGO_BYTES_PER_CELL * NX_PER_GPU * NY_PER_GPU / f_per_launch * 1e-9
+        fast = {"value": cells_total * K / f_seconds * 1e-6, "unit": UNIT, "ms_per_step": f_seconds / K * 1e3,
+                "roofline": {"bound": "hbm", "achieved": f_achieved, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": f_achieved / peak_gbs, "traffic": prof.get("k_fused_step_fast_8192x8192"),
+                             "kernel": "k_fused_step<HLLC, fused dt, fast>", "kernel_ms_per_launch": f_per_launch * 1e3},
+                "arithmetic": "fp64 with explicit FMAs and reciprocal-multiply division (csrc/e2d_fast.cuh); opt-in "
+                              "`[other] arithmetic=fast`; tolerance 1e-12 (tests/test_gpu_fast.py)"}
+        n_fp64 = prof.get("k_fused_step_fast_8192x8192_fp64_warp_inst")
+        if n_fp64:
+            mhz = (clk.summary().get("sm_mhz") or 1965)
+            rate = n_fp64 / f_per_launch / (148 * 4) / (mhz * 1e6)
+            fast["roofline"]["fp64_pipe_frac"] = rate / float(prof.get("fp64_peak_warp_inst_per_clk_per_smsp", 0.476))
+        if not distributed:
+            # deviation of the fast state from the strict one (bit-identical to the reference) after the same W + K
+            # steps of this workload: north_star's metric (euler2d_kokkos_b200/parity.py)
+            from euler2d_kokkos_b200.parity import state_deviation
+
+            cur_w = e2d.HydroRun.U if (W + K) % 2 == 0 else e2d.HydroRun.U2
+            Us = hydro.download(cur_w)[:, 2:-2, 2:-2]
+            Uf = hf.download(cur_w)[:, 2:-2, 2:-2]
+            dev_rows = state_deviation(Uf, Us)
+            del Us, Uf
+            dts_s, dts_f = hydro.dt_history(), hf.dt_history()
+            fast["parity_vs_strict"] = {
+                "steps": W + K, "tolerance": 1e-12,
+                "rel_L1": {n_: l1 for n_, l1, _ in dev_rows}, "rel_Linf": {n_: li for n_, _, li in dev_rows},
+                "dt_rel_max": float(max(abs(a_ - b_) / b_ for a_, b_ in zip(dts_f, dts_s))),
+                "same_step_count": bool(stf.nStep == st.nStep)}
+            hf.close()
+            del hf
 
     # ---------------- e2e: a time march whose state lives in pinned HOST memory, through the streamed host step
     # (e2d_step_host_streamed): every step copies this rank's whole slab host->device, advances it and copies the
@@ -364,7 +422,8 @@ def ours(args):
                 "ms_per_step": seconds / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config_dict(world), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
-                "hbm_gbs_algorithmic": ALGO_BYTES_PER_CELL * cells_total * K / seconds * 1e-9, "impl": "ours"}
+                "hbm_gbs_algorithmic": ALGO_BYTES_PER_CELL * cells_total * K / seconds * 1e-9, "impl": "ours",
+                "fast_arithmetic": fast}
         line.update(extra)
         print(json.dumps(line))
     if distributed:
@@ -380,6 +439,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the `arithmetic=fast` measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
