@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 NX_PER_GPU = 8192
 NY_PER_GPU = 8192
 ALGO_BYTES_PER_CELL = 64  # 4 doubles read + 4 doubles written per cell update
+emit = lambda line: print(json.dumps(line))  # replaced in main(): the one JSON line goes to the real stdout
 METRIC = "Mcell-updates/s (fp64)"
 UNIT = "Mcell-updates/s"
 
@@ -142,7 +143,7 @@ def reference_arm(args):
     nx = ny = 2048
     res = run_reference_sample(nx, ny, args.steps, args.warmup)
     if res is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_dump missing and /root/reference absent"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_dump missing and /root/reference absent"})
         return 0
     ms = res["loop_seconds"] / max(res["timed_steps"], 1) * 1e3
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -154,7 +155,7 @@ def reference_arm(args):
             "gpu_launches": 0,
             "note": "each step is a bounded sample (2048x2048 cells) of the workload; Mcell-updates/s is size "
                     "independent beyond cache"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -176,6 +177,18 @@ def ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    # Pinned host buffers should live on the NUMA node next to this rank's GPU (they are placed where the allocating
+    # thread runs): bind to the GPU's CPU set while allocating, restore afterwards (the CPU baseline uses every core).
+    cpus_before = os.sched_getaffinity(0)
+    numa_bound = False
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa_bound = os.sched_getaffinity(0) != cpus_before
+    except Exception:
+        pass
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -336,6 +349,9 @@ def ours(args):
     nbytes = 4 * jsz * isz * 8
     h_in = torch.empty(4 * jsz * isz, dtype=torch.float64).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
+    h_in.zero_()  # first touch while bound
+    h_out.zero_()
+    os.sched_setaffinity(0, cpus_before)
     cur = e2d.E2D_U if (W + K) % 2 == 0 else e2d.E2D_U2
     e2d.check(e2d.lib().e2d_download(hyd._h, cur, h_in.data_ptr(), e2d.LAYOUT_SOA))
     geo = run.geo if distributed else None
@@ -396,7 +412,8 @@ def ours(args):
            "api": "e2d_step_host_streamed (pinned host state, marched through host memory): per step the whole "
                   "state goes H2D, is advanced by the fused step and comes back D2H, chunked so that both copy "
                   "directions and the kernel overlap; dt threaded from the previous call"
-                  + ("; interface ghost rows + min(dt) exchanged by the caller over NCCL" if distributed else "")}
+                  + ("; interface ghost rows + min(dt) exchanged by the caller over NCCL" if distributed else ""),
+           "host_buffers_numa_local": numa_bound}
     # the same march without overlap (e2d_step_host: H2D, compute_dt, step, D2H in sequence), for comparison
     if not distributed:
         hydro.step_host_ptr(h_in.data_ptr(), h_out.data_ptr())
@@ -425,7 +442,7 @@ def ours(args):
                 "hbm_gbs_algorithmic": ALGO_BYTES_PER_CELL * cells_total * K / seconds * 1e-9, "impl": "ours",
                 "fast_arithmetic": fast}
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -441,6 +458,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the `arithmetic=fast` measurement")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): everything else a library may print on file descriptor 1 (NCCL's
+    # version banner, for instance) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global emit
+    emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)

@@ -511,7 +511,12 @@ k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
     // Publication (e2d_slab.cu): every block fences its stores (peer rows, atomicMax), then three elections by
     // arrival count.  The last block holding the lower / upper edge rows raises the neighbour's halo flag; the
     // last block of the grid copies the finished invDt partial into every rank's slot and raises the invDt flags.
-    __threadfence_system();
+    // (only the edge blocks have peer stores to drain at system scope; for the others the device-scope fence orders
+    //  their atomicMax before their arrival count, which is all the last block's read needs)
+    if (lo || hi)
+      __threadfence_system();
+    else
+      __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
     {

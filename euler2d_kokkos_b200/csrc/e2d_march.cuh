@@ -355,10 +355,10 @@ struct MarchThread
     if (SOLVER == 2)
     {
       // west face of cell (i, r): left = XMAX of (i-1, r), right = XMIN of (i, r) (HydroRunFunctors.h:559-575)
-      hllc_lean<LEAN>(s, a.c, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP],
+      hllc_lean<LEAN, true>(s, a.c, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP],
                       fx[IU], fx[IV], ok);
       // south face of row r: left = YMAX of row r-1, right = YMIN of row r, IU<->IV swapped (:621-640)
-      hllc_lean<LEAN>(s, a.c, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP],
+      hllc_lean<LEAN, true>(s, a.c, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP],
                       fy[IV], fy[IU], ok);
     }
     else
