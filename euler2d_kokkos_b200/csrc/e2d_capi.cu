@@ -1214,11 +1214,45 @@ extern "C"
       E2D_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
       E2D_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     }
+    // Chunk boundaries: jb[k] = first interior row of chunk k, jb[nchunk] = jsize - 2.  Default: ~32 chunks, with the
+    // first two and the last one cut in four — the copy of the first chunks (nothing to overlap with yet) and the way
+    // back of the last one (nothing left to overlap with) are the un-overlapped head and tail of the pipeline.
+    const bool taper = chunk_rows <= 0;
     if (chunk_rows <= 0)
-      chunk_rows = (ny + 31) / 32; // ~32 chunks: the un-overlapped head and tail are ~2/32 of one direction
+      chunk_rows = (ny + 31) / 32;
     if (chunk_rows < 16)
       chunk_rows = 16; // every chunk holds the source rows of the y faces next to it
-    const int nchunk = (ny + chunk_rows - 1) / chunk_rows;
+    std::vector<int> jb;
+    {
+      const int small = chunk_rows / 4 >= 16 ? chunk_rows / 4 : 16;
+      const int n_uniform = (ny + chunk_rows - 1) / chunk_rows;
+      int       j = 2;
+      jb.push_back(j);
+      if (taper && n_uniform >= 8)
+      {
+        const int tail_from = jsize - 2 - 4 * small;
+        for (int k = 0; k < 8 && j + small < tail_from; ++k) // the first two chunks' worth of rows in 8 pieces
+          jb.push_back(j += small);
+        while (j + chunk_rows < tail_from)
+          jb.push_back(j += chunk_rows);
+        if (j < tail_from)
+        {
+          if (tail_from - j < 16 && jb.size() > 1)
+            jb.back() = j = tail_from; // a remainder too short to stand alone extends the chunk before it
+          else
+            jb.push_back(j = tail_from);
+        }
+        while (j + small < jsize - 2)
+          jb.push_back(j += small);
+      }
+      else
+      {
+        while (j + chunk_rows < jsize - 2)
+          jb.push_back(j += chunk_rows);
+      }
+      jb.push_back(jsize - 2);
+    }
+    const int nchunk = (int)jb.size() - 1;
     while ((int)h->ev_pool.size() < 2 * nchunk + 4)
     {
       cudaEvent_t e;
@@ -1229,8 +1263,8 @@ extern "C"
     cudaEvent_t * ev_cmp = h->ev_pool.data() + nchunk; // [nchunk] chunk advanced
     cudaEvent_t   ev_start = h->ev_pool[2 * nchunk], ev_ymin = h->ev_pool[2 * nchunk + 1],
                 ev_fin = h->ev_pool[2 * nchunk + 2];
-    auto first_row = [&](int k) { return 2 + k * chunk_rows; };
-    auto last_row = [&](int k) { return (k == nchunk - 1) ? jsize - 2 : 2 + (k + 1) * chunk_rows; };
+    auto first_row = [&](int k) { return jb[k]; };
+    auto last_row = [&](int k) { return jb[k + 1]; };
     // rows [jlo, jhi) of all four planes
     // the rows of the four variable planes go as ONE 2-D copy (4 "lines" one plane apart): a quarter of the copy
     // calls, 52.3 instead of 54.0 ms per 8192^2 step.  E2D_COPY_PER_PLANE=1 restores one copy per plane.

@@ -332,10 +332,7 @@ struct MarchThread
       trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
       if (!ok)
         trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
-      trace_face_lean<-1>(s, qC, dqX, s0, dtdx, xmin);
-      trace_face_lean<+1>(s, qC, dqX, s0, dtdx, xmax);
-      trace_face_lean<-1>(s, qC, dqY, s0, dtdy, ymin);
-      trace_face_lean<+1>(s, qC, dqY, s0, dtdy, ymax);
+      trace_faces_lean(s, qC, dqX, dqY, s0, dtdx, dtdy, xmin, xmax, ymin, ymax);
     }
 
     st4<PACK>(sm.XMAX[r & 1], t, xmax);
