@@ -427,6 +427,24 @@ def ours(args):
         hydro.close()
         del hydro
         if rank == 0 and not args.no_cpu_baseline:
+            # the reference's own GPU build (real Kokkos/CUDA for sm_100, baseline/build_ref_cuda.sh), when present:
+            # the generic recompiled kernels this library is meant to beat, on the same workload and GPU
+            try:
+                from tools.ref_cuda_perf import run_reference_cuda
+
+                rows = [run_reference_cuda("four_quadrant", NX_PER_GPU, NY_PER_GPU, 20, impl) for impl in (0, 1, 2)]
+                rows = [r for r in rows if r and "error" not in r]
+                if rows:
+                    best = max(rows, key=lambda r: r["Mcell_updates_per_s"])
+                    extra["reference_gpu"] = {
+                        "value": rows[0]["Mcell_updates_per_s"], "unit": UNIT,
+                        "kind": "unmodified reference, Kokkos 5.1.0 CUDA backend (-arch=sm_100), implementationVersion 0 "
+                                "(its default), 20 steps of this workload on this GPU, its own total-time clock",
+                        "best_value": best["Mcell_updates_per_s"],
+                        "best_implementationVersion": best["implementationVersion"],
+                        "by_implementationVersion": {str(r["implementationVersion"]): r["Mcell_updates_per_s"] for r in rows}}
+            except Exception as ex:  # evidence only
+                extra["reference_gpu"] = {"value": None, "error": str(ex)[:200]}
             try:
                 cpu_baseline = run_reference_sample(4096, 4096, 6, 1)
                 if cpu_baseline:
