@@ -416,6 +416,30 @@ def ours(args):
            "host_buffers_numa_local": numa_bound}
     # the same march without overlap (e2d_step_host: H2D, compute_dt, step, D2H in sequence), for comparison
     if not distributed:
+        # and the loop exactly as the reference's main.cpp drives its own GPU build (main.cpp:100-143): the state stays
+        # on the device, per step compute_dt() returns a host scalar and godunov_unsplit(nStep, dt) takes it back
+        try:
+            hp2 = e2d.HydroParams.from_string(deck_text("four_quadrant", **workload_overrides(world),
+                                                        other__implementationVersion=2))
+            with e2d.HydroRun(hp2) as h2:
+                h2.make_boundaries(e2d.HydroRun.U)
+                h2.make_boundaries(e2d.HydroRun.U2)
+                n_ref_loop = max(3, min(K, 20))
+                for n_ in range(2):
+                    h2.godunov_unsplit(n_, h2.compute_dt(n_ % 2))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for n_ in range(2, 2 + n_ref_loop):
+                    h2.godunov_unsplit(n_, h2.compute_dt(n_ % 2))
+                h2.synchronize()
+                t_loop = time.perf_counter() - t0
+            e2e["host_driven_device_resident_loop"] = {
+                "value": cells_total * n_ref_loop / t_loop * 1e-6, "unit": UNIT, "steps": n_ref_loop,
+                "ms_per_step": t_loop / n_ref_loop * 1e3,
+                "api": "compute_dt(useU) -> host double, godunov_unsplit(nStep, dt), implementationVersion 2; state "
+                       "resident on the device as in the reference's own CUDA build (8 B each way per step)"}
+        except Exception as ex:  # evidence only
+            e2e["host_driven_device_resident_loop"] = {"value": None, "error": str(ex)[:200]}
         hydro.step_host_ptr(h_in.data_ptr(), h_out.data_ptr())
         torch.cuda.synchronize()
         t0 = time.perf_counter()
