@@ -75,6 +75,14 @@ struct e2d_handle
   double *     Sy = nullptr; // impl 1
   // scalars
   unsigned long long * d_bits = nullptr; // scratch for compute_dt
+  // compute_dt cache: godunov_unsplit (implementationVersion 2) folds the CFL reduction of the state it writes into
+  // the fused kernel (the same per-cell integrand, bit for bit), so the compute_dt that follows — the reference's
+  // call pattern, main.cpp:128-139 — only fetches 8 bytes instead of re-reading the array.  Valid only while the
+  // library is the sole writer: every entry point that writes an array clears it; it is never used for caller-owned
+  // arrays (U_ext / U2_ext) nor after e2d_device_ptr has handed a pointer out.
+  unsigned long long * d_cfl = nullptr; // [2]: invDt bit patterns of U, U2
+  bool                 cfl_valid[2] = { false, false };
+  bool                 cfl_cache_ok = true;
   LoopState *          d_loop = nullptr;
   LoopState *          h_loop = nullptr; // pinned mirror
   double *             d_hist = nullptr;
@@ -222,10 +230,17 @@ godunov_impl(e2d_handle * h, double * in, double * out, double dt, bool do_bc)
     return rc;
 
   PhaseTimer tg(h, 1);
+  const int w_out = (out == h->U) ? 0 : 1;
+  h->cfl_valid[w_out] = false;
   if (impl == 2)
   {
-    // fused: no deep_copy, no Q array (the reference's impl 2 keeps both, :302,:309,:359)
-    E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, nullptr, nullptr, st));
+    // fused: no deep_copy, no Q array (the reference's impl 2 keeps both, :302,:309,:359); the CFL reduction of the
+    // new state rides along for the next compute_dt (see e2d_handle::d_cfl)
+    unsigned long long * cfl = h->cfl_cache_ok ? h->d_cfl + w_out : nullptr;
+    if (cfl)
+      E2D_CUDA(cudaMemsetAsync(cfl, 0, sizeof(unsigned long long), st));
+    E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, cfl, nullptr, st));
+    h->cfl_valid[w_out] = cfl != nullptr;
     return E2D_OK;
   }
   E2D_CUDA(cudaMemcpyAsync(out, in, h->n * sizeof(double), cudaMemcpyDeviceToDevice, st)); // :302
@@ -558,6 +573,8 @@ extern "C"
         h->own_U2 = true;
       }
       E2D_TRY(cudaMalloc(&h->d_bits, sizeof(unsigned long long)));
+      E2D_TRY(cudaMalloc(&h->d_cfl, 2 * sizeof(unsigned long long)));
+      h->cfl_cache_ok = !U_ext && !U2_ext;
       E2D_TRY(cudaMalloc(&h->d_loop, sizeof(LoopState)));
       E2D_TRY(cudaMallocHost(&h->h_loop, sizeof(LoopState)));
       E2D_TRY(cudaGetDevice(&h->device));
@@ -613,6 +630,7 @@ extern "C"
     cudaFree(h->Sx);
     cudaFree(h->Sy);
     cudaFree(h->d_bits);
+    cudaFree(h->d_cfl);
     cudaFree(h->d_loop);
     for (void * q : h->peers.ipc_opened)
       cudaIpcCloseMemHandle(q);
@@ -662,10 +680,16 @@ extern "C"
       return fail(E2D_ERR_INVALID, "bad argument");
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     const double * A = (useU == 0) ? h->U : h->U2; // HydroRun.h:237-240
-    E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), h->stream));
-    E2D_CUDA(launch_reduce_invdt(h->p, h->g, A, h->d_bits, h->stream));
-    double invDt = 0.0;
-    E2D_CUDA(cudaMemcpyAsync(&invDt, h->d_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const int      w = (useU == 0) ? 0 : 1;
+    double         invDt = 0.0;
+    if (h->cfl_cache_ok && h->cfl_valid[w])
+      E2D_CUDA(cudaMemcpyAsync(&invDt, h->d_cfl + w, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else
+    {
+      E2D_CUDA(cudaMemsetAsync(h->d_bits, 0, sizeof(unsigned long long), h->stream));
+      E2D_CUDA(launch_reduce_invdt(h->p, h->g, A, h->d_bits, h->stream));
+      E2D_CUDA(cudaMemcpyAsync(&invDt, h->d_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
     E2D_CUDA(cudaStreamSynchronize(h->stream));
     if (invdt_local)
       *invdt_local = invDt;
@@ -720,6 +744,7 @@ extern "C"
     E2D_CUDA(cudaSetDevice(h->device));
     if (max_steps < 0)
       max_steps = p.nStepmax;
+    h->cfl_valid[0] = h->cfl_valid[1] = false; // the loop rewrites both arrays
     const unsigned long long launches0 = g_launches.load();
 
     // dt history buffer
@@ -1108,6 +1133,7 @@ extern "C"
       return fail(E2D_ERR_INVALID, "bad argument (array not allocated?)");
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     h->loop_primed = false;
+    h->cfl_valid[0] = h->cfl_valid[1] = false;
     if (layout == E2D_LAYOUT_SOA)
     {
       E2D_CUDA(cudaMemcpyAsync(A, host, h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1126,6 +1152,8 @@ extern "C"
   double *
   e2d_device_ptr(e2d_handle * h, int which)
   {
+    if (h)
+      h->cfl_cache_ok = false; // the caller may write through the pointer: compute_dt re-reads the array from now on
     return h ? array_of(h, which) : nullptr;
   }
 
@@ -1187,6 +1215,7 @@ extern "C"
     if (dt_out)
       *dt_out = h->h_loop->dt;
     h->loop_primed = false;
+    h->cfl_valid[0] = h->cfl_valid[1] = false;
     return E2D_OK;
   }
 
@@ -1385,6 +1414,7 @@ extern "C"
     if (dt_next)
       *dt_next = p.cfl / inv_next; // = compute_dt of the state just written (this slab's rows)
     h->loop_primed = false;
+    h->cfl_valid[0] = h->cfl_valid[1] = false;
     return E2D_OK;
   }
 

@@ -207,7 +207,10 @@ int e2d_destroy(e2d_handle * h);
 
 /* HydroRun::compute_dt(useU) (src/HydroRun.h:229-251): *dt = cfl / max(invDt). Synchronous.
  * On a slab, *invdt_local (may be NULL) returns this rank's partial max so the caller can
- * allreduce(max) it and form dt = cfl/invDt itself. */
+ * allreduce(max) it and form dt = cfl/invDt itself.
+ * When the array was last written by e2d_godunov_unsplit with implementationVersion 2, the reduction has already
+ * been folded into that step's kernel (same integrand per cell, same bits) and only 8 bytes are fetched.  The
+ * shortcut is never taken for caller-owned arrays (U_ext/U2_ext) nor once e2d_device_ptr has handed a pointer out. */
 int e2d_compute_dt(e2d_handle * h, int useU, double * dt, double * invdt_local);
 /* HydroRun::make_boundaries(Udata) (src/HydroRun.h:390-399); which = E2D_U | E2D_U2.
  * On a slab only the faces this rank owns are filled (x always; ymin on rank 0; ymax on the last). */

@@ -499,3 +499,29 @@ def test_driver_executable_matches_reference_report(tmp_path):
     assert_bitwise(arrs["rho"].reshape(48, 64), U_ref[0, 2:-2, 2:-2], "rho in the last snapshot")
     prof = np.load(tmp_path / "sedov_blast_density_profile.npy")
     assert prof.shape == (op.blast_nbins,)
+
+
+def test_compute_dt_cache_after_fused_step_is_exact_and_invalidated():
+    """implementationVersion 2: godunov_unsplit folds the next compute_dt into its kernel (e2d_handle::d_cfl).  The
+    cached value must be the bits a fresh reduction gives, and every other writer of the array must drop it."""
+    hp, op = both_params("implode", mesh__nx=96, mesh__ny=64, other__implementationVersion=2)
+    U_ref, dts_ref, n_ref, _ = oracle.run(op, 12)
+    with HydroRun(hp) as hydro:
+        n, t, dts = host_loop(hydro, hp, 12)          # compute_dt served from the cache from step 1 on
+        assert_bitwise(dts, dts_ref, "dt sequence through the cache")
+        cached = hydro.compute_dt(n % 2)
+        U = hydro.download(HydroRun.U if n % 2 == 0 else HydroRun.U2)
+        assert_bitwise(U[INNER], U_ref[INNER], "state")
+        # overwrite the array through the API: the cache must not survive
+        V = U.copy()
+        V[1] *= 1.5
+        hydro.upload(HydroRun.U if n % 2 == 0 else HydroRun.U2, V)
+        fresh = hydro.compute_dt(n % 2)
+        assert fresh != cached
+        op_dt = op.cfl / oracle.compute_invdt(op, V)
+        assert fresh == op_dt
+        # a pointer handed out disables the shortcut for good
+        hydro.godunov_unsplit(n, fresh)
+        hydro.device_ptr(HydroRun.U)
+        W = hydro.download(HydroRun.U if (n + 1) % 2 == 0 else HydroRun.U2)
+        assert hydro.compute_dt((n + 1) % 2) == op.cfl / oracle.compute_invdt(op, W)
