@@ -829,6 +829,11 @@ extern "C"
     // data on every rank and looked at after the same batches, so all ranks stop together.
     // The flags of this call start one past anything an earlier call's last fused step may have published.
     h->seq += 1;
+    // Single GPU, no per-step event records in between: the two kernels of a step are launched as programmatic
+    // dependents of each other, so their launch latency overlaps the predecessor's tail (it matters on small grids,
+    // where a step is tens of microseconds).  Peers: kept off — their kernels spin on remote flags.
+    static const bool pdl_off = std::getenv("E2D_NO_PDL") != nullptr;
+    const bool        pdl = nranks == 1 && !h->timing && !pdl_off;
     bool first = true;
     bool finished = hs.done != 0;
     while (!finished)
@@ -853,7 +858,7 @@ extern "C"
           E2D_CUDA(launch_slab_push(pa, st));
         }
         first = false;
-        E2D_CUDA(launch_slab_boundaries(p, h->g, in, faces, sa, st));
+        E2D_CUDA(launch_slab_boundaries(p, h->g, in, faces, sa, st, pdl));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
         if (nranks > 1)
@@ -870,7 +875,7 @@ extern "C"
         }
         else
           E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, &h->d_state->dt, &h->d_state->invdt_acc,
-                                     &h->d_state->done, st));
+                                     &h->d_state->done, st, nullptr, nullptr, 2, 0, pdl));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));
       }

@@ -94,8 +94,10 @@ struct SlabStepArgs
 };
 
 cudaError_t launch_slab_push(const SlabPushArgs & a, cudaStream_t st);
+// pdl: programmatic dependent launch — the kernel may be scheduled while its predecessor in the stream drains; it
+// starts with griddepcontrol.wait, so nothing of it runs before the predecessor has completed and flushed
 cudaError_t launch_slab_boundaries(const e2d_params & p, const Geom & g, double * A, int faces, const SlabStepArgs & a,
-                                   cudaStream_t st);
+                                   cudaStream_t st, bool pdl = false);
 cudaError_t launch_slab_finish(const SlabStepArgs & a, cudaStream_t st);
 cudaError_t preload_slab_kernels(); // force-load the loop's kernels (lazy loading may wait for running kernels)
 cudaError_t preload_step_kernels();
@@ -132,7 +134,22 @@ struct MarchPeers
 cudaError_t launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
                               const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done,
                               cudaStream_t st, const MarchPeers * peers = nullptr, FusedLink * link = nullptr,
-                              int j_first = 2, int j_last = 0 /* <= 0: all rows; else rows [j_first, j_last) */);
+                              int j_first = 2, int j_last = 0 /* <= 0: all rows; else rows [j_first, j_last) */,
+                              bool pdl = false /* see launch_slab_boundaries */);
+
+// Programmatic dependent launch (sm_90+).  Both are no-ops in a kernel launched without the attribute.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void
+pdl_wait_for_predecessor()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void
+pdl_release_successor()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 // x-ghost columns of rows [jlo, jhi) (faces & E2D_FACES_X)
 cudaError_t launch_bc_x_rows(const e2d_params & p, const Geom & g, double * U, int faces, int jlo, int jhi,
                              cudaStream_t st);

@@ -452,6 +452,8 @@ template <int SOLVER, bool FUSE_DT, bool LINKED, int MATH = 0>
 __global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
 k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
 {
+  pdl_wait_for_predecessor(); // (no-ops unless launched with the programmatic-serialization attribute)
+  pdl_release_successor();
   if (d_done && *d_done)
     return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1063,7 +1065,7 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
 cudaError_t
 launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
                   const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done, cudaStream_t st,
-                  const MarchPeers * peers, FusedLink * link, int j_first, int j_last)
+                  const MarchPeers * peers, FusedLink * link, int j_first, int j_last, bool pdl)
 {
   MarchArgs a;
   a.Uin = Uin;
@@ -1108,6 +1110,7 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     lk = *link;
   }
   const size_t smem = sizeof(MarchSmem<kBX>);
+  cudaError_t launch_err = cudaSuccess;
 #define E2D_FS1(SOL, FUSE, LINKED, MATH)                                                                     \
   do                                                                                                      \
   {                                                                                                       \
@@ -1123,7 +1126,17 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
         return e;                                                                                         \
       configured = true;                                                                                  \
     }                                                                                                     \
-    k_fused_step<SOL, FUSE, LINKED, MATH><<<grid, kBX, smem, st>>>(a, d_done, lk);                        \
+    cudaLaunchConfig_t cfg_ = {};                                                                         \
+    cfg_.gridDim = grid;                                                                                  \
+    cfg_.blockDim = dim3(kBX);                                                                            \
+    cfg_.dynamicSmemBytes = smem;                                                                         \
+    cfg_.stream = st;                                                                                     \
+    cudaLaunchAttribute at_[1];                                                                           \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                                \
+    cfg_.attrs = at_;                                                                                     \
+    cfg_.numAttrs = pdl ? 1 : 0;                                                                          \
+    launch_err = cudaLaunchKernelEx(&cfg_, k_fused_step<SOL, FUSE, LINKED, MATH>, a, d_done, lk);         \
   } while (0)
 #define E2D_FS(SOL, MATH)               \
   do                                    \
@@ -1146,7 +1159,7 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
 #undef E2D_FS
 #undef E2D_FS1
   count_launch();
-  return cudaGetLastError();
+  return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
 }
 
 cudaError_t

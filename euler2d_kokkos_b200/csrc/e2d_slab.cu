@@ -160,6 +160,8 @@ loop_scalars(const SlabStepArgs & a, bool open_next)
 __global__ void __launch_bounds__(128)
 k_slab_boundaries(Geom g, BcArgs bc, double * __restrict__ A, SlabStepArgs a)
 {
+  pdl_wait_for_predecessor(); // the previous fused step has completed (its state, its invDt partial)
+  pdl_release_successor();    // the fused step behind this kernel may be scheduled; it waits for our completion
   if (threadIdx.x == 0)
   {
     // once the loop is over the fused steps are no-ops and publish nothing: there is nothing to wait for
@@ -217,12 +219,21 @@ launch_slab_push(const SlabPushArgs & a, cudaStream_t st)
 
 cudaError_t
 launch_slab_boundaries(const e2d_params & p, const Geom & g, double * A, int faces, const SlabStepArgs & a,
-                       cudaStream_t st)
+                       cudaStream_t st, bool pdl)
 {
-  const int n = 4 * g.isize + 4 * g.jsize;
-  k_slab_boundaries<<<(n + 127) / 128, 128, 0, st>>>(g, make_bc_args(p, faces), A, a);
+  const int          n = 4 * g.isize + 4 * g.jsize;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((n + 127) / 128));
+  cfg.blockDim = dim3(128);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, k_slab_boundaries, g, make_bc_args(p, faces), A, a);
   count_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t
