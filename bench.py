@@ -233,7 +233,14 @@ def ours(args):
         seconds = st.seconds
         kernel_seconds = st.seconds_step_kernel
         launches = e2d.lib().e2d_kernel_launch_count() - launches0
-        tmax = torch.tensor([seconds, kernel_seconds], dtype=torch.float64, device=dev)
+        mine = torch.tensor([seconds, kernel_seconds], dtype=torch.float64, device=dev)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        # per-rank view of the same loop: every step ends in a global max, so the loop time is common to all ranks
+        # and the slowest rank's kernel sets it; the spread shows how much of the scaling loss is GPU-to-GPU variance
+        extra["per_rank"] = {"fused_kernel_ms_per_launch": [float(e_[1].item()) / K * 1e3 for e_ in every],
+                             "loop_ms_per_step": [float(e_[0].item()) / K * 1e3 for e_ in every]}
+        tmax = mine.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         seconds, kernel_seconds = float(tmax[0].item()), float(tmax[1].item())
         assert st.nStep == W + K

@@ -804,13 +804,20 @@ extern "C"
     pa.upper = h->peers.upper;
     const int faces = faces_for(h);
     FusedLink lk{};
-    if (nranks > 1)
+    // E2D_FORCE_LINKED=1 (development aid): run the peer-publishing instantiation of the step kernel on a single
+    // GPU — no neighbours, it only publishes its invDt partial to its own slot — so that it can be timed and profiled
+    // without a second rank
+    static const bool force_linked = std::getenv("E2D_FORCE_LINKED") != nullptr;
+    const bool        linked = nranks > 1 || force_linked;
+    if (linked)
     {
       lk.cnt = h->d_comm->fused_cnt;
       lk.flag_lo = h->peers.lower >= 0 ? &h->peers.comm[h->peers.lower]->halo_flag[1] : nullptr; // I am its upper
       lk.flag_hi = h->peers.upper >= 0 ? &h->peers.comm[h->peers.upper]->halo_flag[0] : nullptr; // I am its lower
       for (int k = 0; k < kMaxRanks; ++k)
         lk.comm[k] = h->peers.comm[k];
+      if (nranks == 1)
+        lk.comm[0] = h->d_comm;
       lk.nranks = nranks;
       lk.rank = rank;
     }
@@ -861,7 +868,7 @@ extern "C"
         E2D_CUDA(launch_slab_boundaries(p, h->g, in, faces, sa, st, pdl));
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
-        if (nranks > 1)
+        if (linked)
         {
           MarchPeers mp; // the step writes `out`: the array the NEXT step reads, on the neighbours too
           mp.lo = h->peers.lower >= 0 ? h->peers.lowerU[1 - which] : nullptr;

@@ -448,9 +448,80 @@ st_release_sys_u64(unsigned long long * p, unsigned long long v)
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Epilogue of the peer-publishing instantiation (multi-GPU, e2d_slab.cu).  Kept out of line: inlined, its live
+// values and addressing leak into the register allocation of the marching loop (ncu: +17 register moves per row and
+// 4 % of the fast kernel's throughput).
+__device__ __noinline__ void
+publish_to_peers(const MarchArgs & a, const FusedLink & link, bool active, int i, int j0, int j1, bool store)
+{
+  const bool lo = active && a.peer_lo && j0 <= 3 && j1 > 2;
+  const bool hi = active && a.peer_hi && j0 <= a.jsize - 3 && j1 > a.jsize - 4;
+  // Edge segments: every thread copies the edge rows of ITS column (which it stored itself a moment ago: program
+  // order makes them visible to it) into the neighbour's ghost rows of the same-parity array.
+  if ((lo || hi) && store)
+  {
+    const size_t plane = (size_t)a.isize * a.jsize;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      // k = 0, 1: my rows 2, 3 -> the lower neighbour's top ghost rows
+      // k = 2, 3: my last two interior rows -> the upper neighbour's rows 0, 1
+      const bool to_lo = k < 2;
+      const int  jr = to_lo ? 2 + k : a.jsize - 4 + (k - 2);
+      if (!(to_lo ? lo : hi) || jr < j0 || jr >= j1)
+        continue;
+      const double * src = a.Uout + (jr * a.isize + i);
+      const int      jsize_d = to_lo ? a.peer_lo_jsize : a.peer_hi_jsize;
+      const int      jd = to_lo ? jsize_d - 2 + k : k - 2;
+      double *       dst = (to_lo ? a.peer_lo : a.peer_hi) + (jd * a.isize + i);
+      const size_t   plane_d = (size_t)a.isize * jsize_d;
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        dst[v * plane_d] = src[v * plane];
+    }
+  }
+  // Publication (e2d_slab.cu): every block fences its stores (peer rows, atomicMax), then three elections by
+  // arrival count.  The last block holding the lower / upper edge rows raises the neighbour's halo flag; the
+  // last block of the grid copies the finished invDt partial into every rank's slot and raises the invDt flags.
+  // (only the edge blocks have peer stores to drain at system scope; for the others the device-scope fence orders
+  //  their atomicMax before their arrival count, which is all the last block's read needs)
+  if (lo || hi)
+    __threadfence_system();
+  else
+    __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    if (lo && atomicAdd(&link.cnt[0], 1u) == link.n_lo - 1)
+    {
+      link.cnt[0] = 0;
+      __threadfence_system();
+      st_release_sys_u64(link.flag_lo, link.seq_next);
+    }
+    if (hi && atomicAdd(&link.cnt[1], 1u) == link.n_hi - 1)
+    {
+      link.cnt[1] = 0;
+      __threadfence_system();
+      st_release_sys_u64(link.flag_hi, link.seq_next);
+    }
+    if (atomicAdd(&link.cnt[2], 1u) == link.n_all - 1)
+    {
+      link.cnt[2] = 0;
+      __threadfence_system();
+      const unsigned long long part = atomicMax(a.invdt_bits, 0ull); // every block's atomicMax precedes its count
+      for (int k = 0; k < link.nranks; ++k)
+        link.comm[k]->invdt_slot[link.parity_next][link.rank] = part;
+      __threadfence_system();
+      for (int k = 0; k < link.nranks; ++k)
+        st_release_sys_u64(&link.comm[k]->invdt_flag[link.rank], link.seq_next);
+    }
+  }
+}
+
 template <int SOLVER, bool FUSE_DT, bool LINKED, int MATH = 0>
 __global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
-k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
+k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_done,
+             const __grid_constant__ FusedLink link)
 {
   pdl_wait_for_predecessor(); // (no-ops unless launched with the programmatic-serialization attribute)
   pdl_release_successor();
@@ -483,70 +554,7 @@ k_fused_step(MarchArgs a, const int * __restrict__ d_done, FusedLink link)
       block_max_to_global(th.invdt, a.invdt_bits);
   }
   if (LINKED)
-  {
-    const bool lo = active && a.peer_lo && th.j0 <= 3 && th.j1 > 2;
-    const bool hi = active && a.peer_hi && th.j0 <= a.jsize - 3 && th.j1 > a.jsize - 4;
-    // Edge segments: every thread copies the edge rows of ITS column (which it stored itself a moment ago: program
-    // order makes them visible to it) into the neighbour's ghost rows of the same-parity array.
-    if ((lo || hi) && th.store)
-    {
-      const size_t plane = (size_t)a.isize * a.jsize;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-      {
-        // k = 0, 1: my rows 2, 3 -> the lower neighbour's top ghost rows
-        // k = 2, 3: my last two interior rows -> the upper neighbour's rows 0, 1
-        const bool to_lo = k < 2;
-        const int  jr = to_lo ? 2 + k : a.jsize - 4 + (k - 2);
-        if (!(to_lo ? lo : hi) || jr < th.j0 || jr >= th.j1)
-          continue;
-        const double * src = a.Uout + (jr * a.isize + th.i);
-        const int      jsize_d = to_lo ? a.peer_lo_jsize : a.peer_hi_jsize;
-        const int      jd = to_lo ? jsize_d - 2 + k : k - 2;
-        double *       dst = (to_lo ? a.peer_lo : a.peer_hi) + (jd * a.isize + th.i);
-        const size_t   plane_d = (size_t)a.isize * jsize_d;
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          dst[v * plane_d] = src[v * plane];
-      }
-    }
-    // Publication (e2d_slab.cu): every block fences its stores (peer rows, atomicMax), then three elections by
-    // arrival count.  The last block holding the lower / upper edge rows raises the neighbour's halo flag; the
-    // last block of the grid copies the finished invDt partial into every rank's slot and raises the invDt flags.
-    // (only the edge blocks have peer stores to drain at system scope; for the others the device-scope fence orders
-    //  their atomicMax before their arrival count, which is all the last block's read needs)
-    if (lo || hi)
-      __threadfence_system();
-    else
-      __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-      if (lo && atomicAdd(&link.cnt[0], 1u) == link.n_lo - 1)
-      {
-        link.cnt[0] = 0;
-        __threadfence_system();
-        st_release_sys_u64(link.flag_lo, link.seq_next);
-      }
-      if (hi && atomicAdd(&link.cnt[1], 1u) == link.n_hi - 1)
-      {
-        link.cnt[1] = 0;
-        __threadfence_system();
-        st_release_sys_u64(link.flag_hi, link.seq_next);
-      }
-      if (atomicAdd(&link.cnt[2], 1u) == link.n_all - 1)
-      {
-        link.cnt[2] = 0;
-        __threadfence_system();
-        const unsigned long long part = atomicMax(a.invdt_bits, 0ull); // every block's atomicMax precedes its count
-        for (int k = 0; k < link.nranks; ++k)
-          link.comm[k]->invdt_slot[link.parity_next][link.rank] = part;
-        __threadfence_system();
-        for (int k = 0; k < link.nranks; ++k)
-          st_release_sys_u64(&link.comm[k]->invdt_flag[link.rank], link.seq_next);
-      }
-    }
-  }
+    publish_to_peers(a, link, active, th.i, th.j0, th.j1, th.store);
 }
 
 // ------------------------------------------------------------------------------------------
