@@ -190,3 +190,40 @@ def test_fast_step_host_streamed_matches_device_loop():
             used, dt = hydro.step_host_streamed(a, b, dt, 0)
             a, b = b, a
     assert_bitwise(a[INNER], U1, "streamed host march, fast")
+
+
+@pytest.mark.parametrize("bcs", [(3, 3, 3, 3), (3, 3, 2, 1), (2, 1, 3, 3)])
+@pytest.mark.parametrize("slope_type", [0, 1, 2])
+def test_fast_boundary_and_slope_variants(bcs, slope_type):
+    """periodic / absorbing / reflecting mixes and every slope_type the reference handles, within the tolerance"""
+    ov = dict(mesh__nx=72, mesh__ny=56, mesh__boundary_type_xmin=bcs[0], mesh__boundary_type_xmax=bcs[1],
+              mesh__boundary_type_ymin=bcs[2], mesh__boundary_type_ymax=bcs[3], hydro__slope_type=slope_type)
+    hp, op, U, dts, st = run_mode("four_quadrant", "fast", 120, **ov)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 120)
+    assert st.nStep == n_ref
+    np.testing.assert_allclose(dts, dts_ref[1:], rtol=TOL)
+    assert_within_tolerance(U, U_ref[INNER], f"bc {bcs} slope_type {slope_type}")
+
+
+@pytest.mark.parametrize("solver", ["approx", "hll"])
+def test_fast_switch_leaves_the_other_solvers_strict(solver):
+    """only HLLC has a fast form: with honourRiemannSolver the other solvers run the strict kernel, same bits"""
+    ov = dict(mesh__nx=64, mesh__ny=48, hydro__riemann=solver, other__honourRiemannSolver="yes")
+    _, _, Uf, dtf, sf = run_mode("implode", "fast", 30, **ov)
+    _, _, Us, dts, ss = run_mode("implode", "strict", 30, **ov)
+    assert_bitwise(Uf, Us, f"{solver}: arithmetic=fast must not change a solver without a fast form")
+    assert_bitwise(dtf, dts, "dt history")
+
+
+def test_fast_host_driven_loop_matches_device_loop():
+    """compute_dt / godunov_unsplit (implementationVersion 2) in fast mode: the first dt comes from the strict
+    reduction kernel, every later one from the fused step's own CFL fold — the same sequence as e2d_run"""
+    from test_gpu_hydro_run import host_loop
+
+    hp, op, U1, dts1, st1 = run_mode("blast", "fast", 25, mesh__nx=64, mesh__ny=96, other__implementationVersion=2)
+    with HydroRun(hp) as hydro:
+        n, t, dts = host_loop(hydro, hp, 25)
+        U = hydro.download(HydroRun.U if n % 2 == 0 else HydroRun.U2)
+    assert n == st1.nStep and t == st1.t
+    assert_bitwise(dts[1:], dts1, "dt sequence")
+    assert_bitwise(U[INNER], U1, "state")
