@@ -208,11 +208,14 @@ def ours(args):
         hydro = e2d.HydroRun(hp)
         hydro.enable_timers(True)  # one event pair around each fused-step launch (no extra syncs)
         hydro.run(W)
+        clk = ClockSampler(local_rank)
+        clk.__enter__()  # NVML start-up happens BEFORE the barrier: it must not delay this rank's entry into the loop
         barrier()
+        clk.samples.clear()  # keep only the samples taken under load
         launches0 = e2d.lib().e2d_kernel_launch_count()
-        with ClockSampler(local_rank) as clk:
-            st = hydro.run(W + K)
+        st = hydro.run(W + K)
         barrier()
+        clk.__exit__(None, None, None)
         seconds = st.seconds
         kernel_seconds = st.seconds_step_kernel
         launches = e2d.lib().e2d_kernel_launch_count() - launches0
@@ -225,11 +228,16 @@ def ours(args):
         run = PeerSlabRun(hp, device=dev)
         run.hydro.enable_timers(True)
         run.run(W)
+        # NVML start-up (tens of milliseconds, different on every rank) happens BEFORE the barrier: a rank that enters
+        # the loop late makes all the others wait for its first halo rows inside their timed region
+        clk = ClockSampler(local_rank)
+        clk.__enter__()
         barrier()
+        clk.samples.clear()  # keep only the samples taken under load
         launches0 = e2d.lib().e2d_kernel_launch_count()
-        with ClockSampler(local_rank) as clk:
-            st = run.run(W + K)
-            barrier()
+        st = run.run(W + K)
+        barrier()
+        clk.__exit__(None, None, None)
         seconds = st.seconds
         kernel_seconds = st.seconds_step_kernel
         launches = e2d.lib().e2d_kernel_launch_count() - launches0
