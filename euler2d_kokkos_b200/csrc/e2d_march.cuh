@@ -6,12 +6,13 @@
 //      publishes the XMAX face state (for the east neighbour) and parks the YMAX face state (for
 //      its own next row);
 //   -- one __syncthreads --
-//   B) solves the x-face Riemann problem (west face of (i, r)) and the y-face one (south face) back
-//      to back in one straight-line block, so the two solves, the CFL integrand of the row being
-//      completed and the primitive conversion of the row being fetched overlap in the FP64 pipe;
-//      publishes the x flux, completes the conservative update of row r-1 (its east x flux and
-//      north y flux are now known), stores it, folds the next step's CFL reduction in, and
-//      converts row r+2 (loaded at the top of the phase) to primitives into the ring.
+//   B) reads its ring rows and at once issues the asynchronous fetch (cp.async) of row r+3 into the
+//      slot just read; solves the x-face Riemann problem (west face of (i, r)) and the y-face one
+//      (south face) back to back in one straight-line block, so the two solves, the CFL integrand of
+//      the row completed one phase earlier and the primitive conversion of row r+2 overlap in the
+//      FP64 pipe; publishes the x flux, completes the conservative update of row r-1 (its east x
+//      flux and north y flux are now known), stores it, folds the next step's CFL reduction in, and
+//      writes the primitives of row r+2 into the ring.
 //
 // Each cell's slopes and trace are computed exactly once, each face's Riemann problem exactly once
 // (the reference's flux kernel computes 3 slope sets, 4 traces and 2 solves per cell,
@@ -20,7 +21,8 @@
 // order of UpdateFunctor (src/HydroRunFunctors.h:695-713) with fluxes pre-scaled by dt/dx, dt/dy
 // (:572-575,:637-640), so the result is bit-identical to the reference's implementation 0.
 //
-// Shared memory (ring slots are row % 3 or row & 1; one barrier per row suffices):
+// Shared memory (ring slots are row % 3 or row & 1; one barrier per row suffices; each row of
+// states is four planes of doubles in the strict kernel, two planes of 16-byte pairs in the fast one):
 //   Q[r%3]       primitives of rows r-1, r, r+1      written in B(r-2)   read in A(r-1..r+1)
 //   RY[r%3]      refined 1/rho of the same rows      own column only
 //   U[r%3]       conservatives of rows r, r+1, r+2   own column only     row r+3 is fetched by cp.async issued in

@@ -43,3 +43,4 @@ def both():
 for name, fn in (("H2D alone", h2d), ("D2H alone", d2h), ("H2D + D2H concurrently", both)):
     t = timed(fn)
     print(f"{name:26s} {t*1e3:7.2f} ms  {nbytes/t*1e-9:6.1f} GB/s per direction", flush=True)
+
