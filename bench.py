@@ -522,6 +522,17 @@ def main():
     os.dup2(2, 1)
     global emit
     emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: become the torchrun command the contract describes
+        import socket
+
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        os.dup2(real_stdout.fileno(), 1)
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                                  str(args.gpus), "--master-addr", "127.0.0.1", "--master-port", str(port),
+                                  os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)
