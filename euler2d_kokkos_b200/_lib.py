@@ -45,7 +45,8 @@ class Params(C.Structure):
                                      "postshock_density", "postshock_pressure", "postshock_velocity",
                                      "shock_loc")]
         + [("implementationVersion", C.c_int), ("outputDir", C.c_char * 256), ("outputPrefix", C.c_char * 256),
-           ("honourRiemannSolver", C.c_int), ("vtkAppended", C.c_int), ("arithmetic", C.c_int)]
+           ("honourRiemannSolver", C.c_int), ("vtkAppended", C.c_int), ("arithmetic", C.c_int),
+           ("unfusedKernels", C.c_int)]
     )
 
     def as_dict(self):

@@ -225,21 +225,33 @@ godunov_impl(e2d_handle * h, double * in, double * out, double dt, bool do_bc)
     PhaseTimer tb(h, 0);
     E2D_CUDA(launch_make_boundaries(p, h->g, in, faces_for(h), nullptr, st)); // :296
   }
-  const int impl = p.implementationVersion;
-  if (int rc = ensure_scratch(h, impl))
-    return rc;
+  const int  impl = p.implementationVersion;
+  const bool fused = impl == 2 || !p.unfusedKernels;
+  if (!fused)
+    if (int rc = ensure_scratch(h, impl))
+      return rc;
 
   PhaseTimer tg(h, 1);
   const int w_out = (out == h->U) ? 0 : 1;
   h->cfl_valid[w_out] = false;
-  if (impl == 2)
+  if (fused)
   {
     // fused: no deep_copy, no Q array (the reference's impl 2 keeps both, :302,:309,:359); the CFL reduction of the
-    // new state rides along for the next compute_dt (see e2d_handle::d_cfl)
+    // new state rides along for the next compute_dt (see e2d_handle::d_cfl).
+    // Implementations 0 and 1 (bit-identical to each other in the reference) produce this very interior and leave
+    // in's ghost cells in out (deep_copy, :302): the fused step + a copy of the ghost frame is the same array.
     unsigned long long * cfl = h->cfl_cache_ok ? h->d_cfl + w_out : nullptr;
     if (cfl)
       E2D_CUDA(cudaMemsetAsync(cfl, 0, sizeof(unsigned long long), st));
-    E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, cfl, nullptr, st));
+    if (impl == 0)
+    {
+      PhaseTimer tf(h, 3); // the reference times its flux kernel for implementation 0 only (:316-320)
+      E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, cfl, nullptr, st));
+    }
+    else
+      E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, cfl, nullptr, st));
+    if (impl != 2)
+      E2D_CUDA(launch_copy_ghost_frame(h->g, in, out, st));
     h->cfl_valid[w_out] = cfl != nullptr;
     return E2D_OK;
   }

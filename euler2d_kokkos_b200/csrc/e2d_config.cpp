@@ -262,6 +262,7 @@ setup(const Config & cfg, e2d_params * p)
     p->implementationVersion = 0;
   }
   p->honourRiemannSolver = cfg.boolean("OTHER", "honourRiemannSolver", false) ? 1 : 0;
+  p->unfusedKernels = cfg.boolean("OTHER", "unfusedKernels", false) ? 1 : 0;
   {
     const std::string ar = cfg.string("OTHER", "arithmetic", "strict");
     p->arithmetic = (ar == "fast") ? E2D_ARITH_FAST : E2D_ARITH_STRICT;

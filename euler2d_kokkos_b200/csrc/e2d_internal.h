@@ -150,6 +150,8 @@ pdl_release_successor()
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #endif
+// out's two-cell ghost frame <- in's (what the reference's deep_copy(out, in) leaves there, src/HydroRun.h:302)
+cudaError_t launch_copy_ghost_frame(const Geom & g, const double * in, double * out, cudaStream_t st);
 // x-ghost columns of rows [jlo, jhi) (faces & E2D_FACES_X)
 cudaError_t launch_bc_x_rows(const e2d_params & p, const Geom & g, double * U, int faces, int jlo, int jhi,
                              cudaStream_t st);

@@ -210,6 +210,35 @@ k_bc_x_rows(Geom g, BcArgs a, double * __restrict__ U, int jlo, int jhi)
     bc_fill_cell(g, a, U, 4 * g.isize + 4 * jlo + k);
 }
 
+// The two-cell frame of ghost cells, copied from `in` to `out`: the part of the reference's deep_copy(data_out,
+// data_in) (src/HydroRun.h:302) that survives the update, which only rewrites the interior.
+__global__ void __launch_bounds__(128)
+k_copy_ghost_frame(Geom g, const double * __restrict__ in, double * __restrict__ out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int       i, j;
+  if (k < 4 * g.isize)
+  { // rows 0, 1, jsize-2, jsize-1, full width
+    const int r = k / g.isize;
+    i = k - r * g.isize;
+    j = r < 2 ? r : g.jsize - 4 + r;
+  }
+  else
+  { // columns 0, 1, isize-2, isize-1 of the rows in between
+    const int kk = k - 4 * g.isize;
+    if (kk >= 4 * (g.jsize - 4))
+      return;
+    const int c = kk & 3;
+    j = 2 + (kk >> 2);
+    i = c < 2 ? c : g.isize - 4 + c;
+  }
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const size_t o = (size_t)j * g.isize + i;
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    out[o + v * plane] = in[o + v * plane];
+}
+
 // ------------------------------------------------------------------------------------------
 // CFL reduction: ComputeDtFunctor, src/HydroRunFunctors.h:17-79.
 // max is exact and order independent, so any reduction tree reproduces the reference's value.
@@ -933,6 +962,15 @@ launch_bc_x_rows(const e2d_params & p, const Geom & g, double * U, int faces, in
     return cudaSuccess;
   const int n = 4 * (jhi - jlo);
   k_bc_x_rows<<<(n + 127) / 128, 128, 0, st>>>(g, make_bc_args(p, faces & E2D_FACES_X), U, jlo, jhi);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t
+launch_copy_ghost_frame(const Geom & g, const double * in, double * out, cudaStream_t st)
+{
+  const int n = 4 * g.isize + 4 * (g.jsize - 4);
+  k_copy_ghost_frame<<<(n + 127) / 128, 128, 0, st>>>(g, in, out);
   count_launch();
   return cudaGetLastError();
 }

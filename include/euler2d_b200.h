@@ -83,9 +83,17 @@ typedef struct e2d_params
    * bit-identical to the reference's Kokkos/OpenMP x86 build.  1 = fast: the fused step evaluates the same
    * formulas with fused multiply-adds and reciprocal-multiply division (csrc/e2d_fast.cuh); results agree with
    * the reference to north_star's tolerance (relative L1/Linf <= 1e-12 per conserved variable, same step
-   * count), not bit for bit.  Only the fused path (implementationVersion 2 / e2d_run / e2d_step_host*) and the
-   * HLLC solver have a fast form; everything else ignores the switch. */
+   * count), not bit for bit.  Only the fused step kernel (e2d_godunov_unsplit unless `unfusedKernels`, e2d_run,
+   * e2d_step_host*) with the HLLC solver has a fast form; everything else ignores the switch. */
   int    arithmetic;
+  /* extension: `[other] unfusedKernels=yes` makes e2d_godunov_unsplit run implementationVersion 0 / 1 as the
+   * reference's literal kernel sequence (deep_copy, ConvertToPrimitives, ComputeAndStoreFluxes + Update, or the
+   * slopes / trace / update-per-direction trio; Q, flux and slope arrays allocated).  Default 0: the fused step kernel
+   * followed by a copy of the ghost frame computes the very same output array — every bit, ghost cells included
+   * (implementations 0 and 1 are bit-identical in the reference) — at 64 instead of 384 bytes of HBM
+   * traffic per cell, so the reference's decks (all implementationVersion 0) run at full speed.  The operator-level
+   * kernels stay available either way as e2d_k_*. */
+  int    unfusedKernels;
 } e2d_params;
 
 /* ------------------------------------------------------------------------------------------ */

@@ -154,8 +154,24 @@ def test_fast_against_strict_large(deck, nx, ny, steps):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-def test_unfused_implementations_ignore_the_switch(impl):
-    """implementationVersion 0 / 1 through godunov_unsplit have no fast form: they stay bit-identical"""
+def test_literal_kernel_sequences_ignore_the_switch(impl):
+    """`unfusedKernels=yes`: implementationVersion 0 / 1 as the reference's own kernel sequence have no fast form and
+    stay bit-identical whatever `arithmetic` says"""
+    from test_gpu_hydro_run import host_loop
+
+    hp, op = both_params("implode", mesh__nx=64, mesh__ny=48, other__implementationVersion=impl,
+                         other__arithmetic="fast", other__unfusedKernels="yes")
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 20)
+    with HydroRun(hp) as hydro:
+        n, t, dts = host_loop(hydro, hp, 20)
+        U = hydro.download(HydroRun.U if n % 2 == 0 else HydroRun.U2)
+    assert_bitwise(U[INNER], U_ref[INNER], f"impl {impl}")
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_fast_through_default_routing_of_implementations_0_and_1(impl):
+    """by default godunov_unsplit runs implementations 0 / 1 through the fused kernel (+ ghost-frame copy), so
+    `arithmetic=fast` applies: within the tolerance, and the ghost frame is still exactly in's"""
     from test_gpu_hydro_run import host_loop
 
     hp, op = both_params("implode", mesh__nx=64, mesh__ny=48, other__implementationVersion=impl,
@@ -164,7 +180,13 @@ def test_unfused_implementations_ignore_the_switch(impl):
     with HydroRun(hp) as hydro:
         n, t, dts = host_loop(hydro, hp, 20)
         U = hydro.download(HydroRun.U if n % 2 == 0 else HydroRun.U2)
-    assert_bitwise(U[INNER], U_ref[INNER], f"impl {impl}")
+        V = hydro.download(HydroRun.U2 if n % 2 == 0 else HydroRun.U)  # the array the last step read
+    assert n == n_ref
+    np.testing.assert_allclose(dts, dts_ref, rtol=TOL)
+    assert_within_tolerance(U[INNER], U_ref[INNER], f"impl {impl}, fast")
+    frame = np.ones(U.shape, bool)
+    frame[INNER] = False
+    assert_bitwise(U[frame], V[frame], "ghost frame = the input's (deep_copy semantics)")
 
 
 @pytest.mark.parametrize("nslabs", [2, 3])

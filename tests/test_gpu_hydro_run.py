@@ -34,11 +34,16 @@ def host_loop(hydro, params, max_steps):
     return n, t, np.array(dts)
 
 
+@pytest.mark.parametrize("unfused", ["no", "yes"])
 @pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("deck", list(SMALL))
-def test_host_driven_loop_bit_exact(deck, impl):
+def test_host_driven_loop_bit_exact(deck, impl, unfused):
+    """`unfused=yes`: implementations 0 / 1 as the reference's literal kernel sequence; `no` (default): the fused
+    step + ghost-frame copy — the same array, ghost cells included, either way."""
     nx, ny = SMALL[deck]
-    hp, op = both_params(deck, mesh__nx=nx, mesh__ny=ny, other__implementationVersion=impl)
+    hp, op = both_params(deck, mesh__nx=nx, mesh__ny=ny, other__implementationVersion=impl,
+                         other__unfusedKernels=unfused)
+    assert hp.unfusedKernels == (1 if unfused == "yes" else 0)
     steps = 40
     U_ref, dts_ref, n_ref, t_ref = oracle.run(op, steps)
     with HydroRun(hp) as hydro:
@@ -201,8 +206,9 @@ def test_save_vtk_matches_reference_format(tmp_path):
     np.testing.assert_allclose(rho, U[0][2:-2, 2:-2].ravel(), rtol=1e-5)  # 6 significant digits, like the reference
 
 
-def test_timers_accumulate():
-    hp, _ = both_params("implode", mesh__nx=64, mesh__ny=64)
+@pytest.mark.parametrize("unfused", ["no", "yes"])
+def test_timers_accumulate(unfused):
+    hp, _ = both_params("implode", mesh__nx=64, mesh__ny=64, other__unfusedKernels=unfused)
     with HydroRun(hp) as hydro:
         hydro.enable_timers(True)
         for n in range(4):
@@ -262,7 +268,7 @@ def test_full_size_8192_properties():
         Uf = fused.download(HydroRun.U2)
         dts = fused.dt_history()
         dt_next = fused.compute_dt(1)
-    hp0, _ = both_params("four_quadrant", mesh__nx=8192, mesh__ny=8192, run__nOutput=-1)
+    hp0, _ = both_params("four_quadrant", mesh__nx=8192, mesh__ny=8192, run__nOutput=-1, other__unfusedKernels="yes")
     with HydroRun(hp0) as unfused:
         n, t, dts0 = host_loop(unfused, hp0, 3)
         U0 = unfused.download(HydroRun.U2)
