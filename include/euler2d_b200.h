@@ -110,7 +110,7 @@ unsigned long long e2d_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* parameters: ConfigMap + HydroParams::setup + HydroParams::init                             */
-/*   replaces config/ConfigMap.{h,cpp}, config/inih/*, src/HydroParams.cpp:43-190             */
+/*   replaces config/ConfigMap.{h,cpp}, config/inih/, src/HydroParams.cpp:43-190               */
 /*   (all reals go through strtof, exactly like ConfigMap::getFloat)                          */
 /* ------------------------------------------------------------------------------------------ */
 int e2d_params_from_ini(const char * path, e2d_params * out);
