@@ -36,14 +36,16 @@ fmadd(double a, double b, double c)
 #endif
 }
 
-// fmax(x, f) for a floor f > 0 (smallr, rho*smallp, smallc: 1e-10 .. 1e-20 guards), decided on the high words: one
-// integer compare instead of a DSETP on the FP64 pipe.  Identical to fmax unless x lies within 2^-20 (relative) above
-// the floor itself, where the floor is returned — states that small are outside the tolerance's meaning anyway.
+// fmax(x, f) for a floor f > 0 (smallr, rho*smallp, smallc: guards of 1e-10 .. 1e-20) as ONE integer instruction: the
+// signed maximum of the two high words (a double's bit pattern orders like a signed integer for non-negative values,
+// and every negative x has a negative high word), low word of x kept.  x >= f comes back untouched; below the floor
+// the result is f up to a relative 2^-20 — an absolute difference of 1e-16 at most, in a value that is an arbitrary
+// guard to begin with.
 E2D_HD double
 floor_at(double x, double f)
 {
 #if E2D_LEAN_DEVICE
-  return (__double2hiint(x) > __double2hiint(f)) ? x : f;
+  return __hiloint2double(max(__double2hiint(x), __double2hiint(f)), __double2loint(x));
 #else
   return x > f ? x : f;
 #endif
@@ -160,12 +162,14 @@ slope(double slope_type, double q, double qPlus, double qMinus)
   return (fabs(dcen) < fabs(sel)) ? dcen : sel;
 }
 
+// slope_type outside {1, 2}: zero slopes (src/HydroBaseFunctor.h:486-500), by multiplying with 0 — `st_or_zero` is
+// slope_type when the limiter applies, else 0: every candidate then loses against sel = +-0, no select needed
 E2D_HD void
-slopes(double slope_type, bool limited, const double q[4], const double qPlus[4], const double qMinus[4], double dq[4])
+slopes(double st_or_zero, const double q[4], const double qPlus[4], const double qMinus[4], double dq[4])
 {
 #pragma unroll
   for (int v = 0; v < 4; ++v)
-    dq[v] = limited ? slope(slope_type, q[v], qPlus[v], qMinus[v]) : 0.0;
+    dq[v] = slope(st_or_zero, q[v], qPlus[v], qMinus[v]);
 }
 
 // trace_unsplit_2d_along_dir (src/HydroBaseFunctor.h:245-289), all four faces of one cell.  n0 = -s0 (the source

@@ -817,8 +817,8 @@ k_eval(Settings s, int func, const double * __restrict__ in, double * __restrict
       const double * a = in + 20 * r;
       double *       o = out + 8 * r;
       const bool     limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
-      fast::slopes(s.slope_type, limited, a, a + 4, a + 8, o);
-      fast::slopes(s.slope_type, limited, a, a + 12, a + 16, o + 4);
+      fast::slopes(limited ? s.slope_type : 0.0, a, a + 4, a + 8, o);
+      fast::slopes(limited ? s.slope_type : 0.0, a, a + 12, a + 16, o + 4);
       break;
     }
     case 17:

@@ -321,8 +321,9 @@ struct MarchThread
     const bool limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
     if (MATH == 1)
     {
-      fast::slopes(s.slope_type, limited, qC, qE, qW, dqX);
-      fast::slopes(s.slope_type, limited, qC, qN, qS, dqY);
+      const double st0 = limited ? s.slope_type : 0.0;
+      fast::slopes(st0, qC, qE, qW, dqX);
+      fast::slopes(st0, qC, qN, qS, dqY);
       fast::trace(s, qC, rd.y, dqX, dqY, hdtdx, hdtdy, xmin, xmax, ymin, ymax);
     }
     else
