@@ -48,6 +48,41 @@ bc_source_hi(int bc, int k, int n, double & sign, bool is_normal)
   return k - n; // periodic
 }
 
+// Source of ghost cell (i, j): the interior cell (i0, j0) it copies, whether it lies in an x / y ghost strip of an
+// active face, and whether the normal momentum changes sign there (reflecting wall).  (i, j) interior: itself.
+__device__ __forceinline__ void
+bc_map(const Geom & g, const BcArgs & a, int i, int j, int & i0, int & j0, bool & in_x, bool & in_y, bool & flip_u,
+       bool & flip_v)
+{
+  const int nx = g.nx, ny = g.ny;
+  in_x = (i < 2 && (a.faces & 1)) || (i >= nx + 2 && (a.faces & 2));
+  in_y = (j < 2 && (a.faces & E2D_FACES_YMIN)) || (j >= ny + 2 && (a.faces & E2D_FACES_YMAX));
+  i0 = i;
+  j0 = j;
+  double sx = 1.0, sy = 1.0;
+  if (in_x)
+    i0 = (i < 2) ? bc_source_lo(a.bc_xmin, i, nx, sx, true) : bc_source_hi(a.bc_xmax, i, nx, sx, true);
+  if (in_y)
+    j0 = (j < 2) ? bc_source_lo(a.bc_ymin, j, ny, sy, true) : bc_source_hi(a.bc_ymax, j, ny, sy, true);
+  flip_u = sx < 0.0;
+  flip_v = sy < 0.0;
+}
+
+// value of ghost cell (i, j), variable v, from array U:  (U(i0, j0) * sign_x) * sign_y, the composition the
+// reference's XMIN, XMAX -> YMIN, YMAX sequence produces (multiplying by +-1.0 is exact)
+__device__ __forceinline__ double
+bc_value(const double * __restrict__ U, size_t src, int v, bool in_x, bool in_y, bool flip_u, bool flip_v)
+{
+  // .cg: the source may be a halo row that a peer GPU stored while this kernel was already running, or a cell another
+  // thread of this block has just written
+  double val = __ldcg(U + src);
+  if (in_x)
+    val = val * ((v == IU && flip_u) ? -1.0 : 1.0);
+  if (in_y)
+    val = val * ((v == IV && flip_v) ? -1.0 : 1.0);
+  return val;
+}
+
 // ghost cell number k of the slab (k < 4*isize: the y-ghost rows, full width; then the x-ghost columns)
 __device__ __forceinline__ void
 bc_fill_cell(const Geom & g, const BcArgs & a, double * __restrict__ U, int k)
@@ -57,8 +92,7 @@ bc_fill_cell(const Geom & g, const BcArgs & a, double * __restrict__ U, int k)
   const int    n_y = 4 * g.isize; // y-ghost rows, full width (i fastest)
   const int    n_x = 4 * g.jsize; // x-ghost columns
 
-  int  i, j;
-  bool in_x_ghost, in_y_ghost;
+  int i, j;
   if (k < n_y)
   {
     const int gsel = k / g.isize;
@@ -82,26 +116,13 @@ bc_fill_cell(const Geom & g, const BcArgs & a, double * __restrict__ U, int k)
   else
     return;
 
-  in_x_ghost = (i < 2 && (a.faces & 1)) || (i >= nx + 2 && (a.faces & 2));
-  in_y_ghost = (j < 2 && (a.faces & E2D_FACES_YMIN)) || (j >= ny + 2 && (a.faces & E2D_FACES_YMAX));
-
+  int  i0, j0;
+  bool in_x, in_y, flip_u, flip_v;
+  bc_map(g, a, i, j, i0, j0, in_x, in_y, flip_u, flip_v);
 #pragma unroll
   for (int v = 0; v < 4; ++v)
-  {
-    double sx = 1.0, sy = 1.0;
-    int    i0 = i, j0 = j;
-    if (in_x_ghost)
-      i0 = (i < 2) ? bc_source_lo(a.bc_xmin, i, nx, sx, v == IU) : bc_source_hi(a.bc_xmax, i, nx, sx, v == IU);
-    if (in_y_ghost)
-      j0 = (j < 2) ? bc_source_lo(a.bc_ymin, j, ny, sy, v == IV) : bc_source_hi(a.bc_ymax, j, ny, sy, v == IV);
-    // .cg: the source may be a halo row that a peer GPU stored while this kernel was already running
-    double val = __ldcg(U + ((size_t)i0 + (size_t)g.isize * j0 + v * plane));
-    if (in_x_ghost)
-      val = val * sx;
-    if (in_y_ghost)
-      val = val * sy;
-    U[(size_t)i + (size_t)g.isize * j + v * plane] = val;
-  }
+    U[(size_t)i + (size_t)g.isize * j + v * plane] =
+      bc_value(U, (size_t)i0 + (size_t)g.isize * j0 + v * plane, v, in_x, in_y, flip_u, flip_v);
 }
 
 inline BcArgs

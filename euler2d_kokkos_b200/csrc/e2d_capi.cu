@@ -94,6 +94,7 @@ struct e2d_handle
   SlabState *          d_state = nullptr;
   SlabState *          h_state = nullptr; // pinned mirror
   unsigned long long   seq = 0;           // steps issued through the slab loop so far (flags carry seq)
+  bool                 seq_poisoned = false; // a wait for a peer timed out: flags and state are no longer trustworthy
   struct
   {
     bool       connected = false;
@@ -604,12 +605,22 @@ extern "C"
             rc = fail(E2D_ERR_CUDA, "cudaEventCreate");
       if (rc != E2D_OK)
         break;
+      // A periodic y direction split over several ranks is closed by the halo exchange between the first and the
+      // last rank: that needs BOTH faces periodic (the reference reads each face on its own and would wrap one side
+      // only, src/HydroRunFunctors.h:1968-2019 — a combination no deck uses and no rank pair could serve).
+      if (!h->whole && (p->boundary_type_ymin == E2D_BC_PERIODIC) != (p->boundary_type_ymax == E2D_BC_PERIODIC))
+      {
+        rc = fail(E2D_ERR_UNSUPPORTED, "y-slabs need boundary_type_ymin and boundary_type_ymax both periodic or neither");
+        break;
+      }
       // HydroRun.h:185-214: initial condition, then U2 = U
       if (p->problemType == E2D_PROBLEM_BLAST && p->blast_total_energy_inside > 0 && !h->whole)
       {
         rc = fail(E2D_ERR_UNSUPPORTED, "energy-renormalised blast init needs the whole domain on one device");
         break;
       }
+      (void)refined_reciprocal(p->dx); // warm the cache: launches inside the loops must never synchronise
+      (void)refined_reciprocal(p->dy);
       E2D_TRY(launch_init_problem(*p, h->g, h->U, h->stream));
       E2D_TRY(cudaMemcpyAsync(h->U2, h->U, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
       E2D_TRY(cudaStreamSynchronize(h->stream));
@@ -743,6 +754,33 @@ extern "C"
     return godunov_impl(h, h->U2, h->U, dt, false);
   }
 
+  // dt history: device buffer of at most kHistMax entries (steps beyond it are not recorded: a run of 10^8 steps must
+  // not allocate 800 MB of history), grown geometrically; never reallocated while a peer may be spinning
+  static const long kHistMax = 1l << 20;
+  static int
+  ensure_history(e2d_handle * h, long want)
+  {
+    if (want > kHistMax)
+      want = kHistMax;
+    if (want < 1024)
+      want = 1024;
+    if (h->hist_cap >= want)
+      return E2D_OK;
+    long cap = h->hist_cap > 0 ? h->hist_cap : 1024;
+    while (cap < want)
+      cap *= 2;
+    double * nh = nullptr;
+    E2D_CUDA(cudaMalloc(&nh, sizeof(double) * cap));
+    E2D_CUDA(cudaMemsetAsync(nh, 0, sizeof(double) * cap, h->stream));
+    if (h->d_hist)
+      E2D_CUDA(cudaMemcpyAsync(nh, h->d_hist, sizeof(double) * h->hist_cap, cudaMemcpyDeviceToDevice, h->stream));
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_hist);
+    h->d_hist = nh;
+    h->hist_cap = cap;
+    return E2D_OK;
+  }
+
   int
   e2d_run(e2d_handle * h, long max_steps, e2d_run_stats * stats)
   {
@@ -756,39 +794,37 @@ extern "C"
     E2D_CUDA(cudaSetDevice(h->device));
     if (max_steps < 0)
       max_steps = p.nStepmax;
+    if (max_steps > 2147483647l)
+      max_steps = 2147483647l; // nStep is an int, like the reference's (main.cpp:61)
     h->cfl_valid[0] = h->cfl_valid[1] = false; // the loop rewrites both arrays
     const unsigned long long launches0 = g_launches.load();
+    if (h->seq_poisoned)
+      return fail(E2D_ERR_CUDA, "slab loop: an earlier e2d_run on this handle lost a peer; the state is invalid");
 
-    // dt history buffer
-    if (h->hist_cap < max_steps + 1)
-    {
-      double * nh = nullptr;
-      long     cap = max_steps + 64;
-      E2D_CUDA(cudaMalloc(&nh, sizeof(double) * cap));
-      E2D_CUDA(cudaMemsetAsync(nh, 0, sizeof(double) * cap, st));
-      if (h->d_hist)
-      {
-        E2D_CUDA(cudaMemcpyAsync(nh, h->d_hist, sizeof(double) * h->hist_cap, cudaMemcpyDeviceToDevice, st));
-        E2D_CUDA(cudaStreamSynchronize(st));
-        cudaFree(h->d_hist);
-      }
-      h->d_hist = nh;
-      h->hist_cap = cap;
-    }
+    // dt history buffer (slabs: sized at connect time, see prepare_slab_loop)
+    if (nranks == 1)
+      if (int rc = ensure_history(h, max_steps + 1))
+        return rc;
 
     // prime the loop state: (t, nStep) from the handle, invDt partial of the current array (main.cpp:128)
-    SlabState & hs = *h->h_state;
+    // E2D_FORCE_LINKED=1 (development aid): run the peer-publishing instantiation of the step kernel on a single
+    // GPU — no neighbours, it only publishes its invDt partial to its own slot — so that it can be timed and profiled
+    // without a second rank.  E2D_TWO_LAUNCH=1: the round-1 single-GPU loop (boundary kernel + step kernel).
+    static const bool force_linked = std::getenv("E2D_FORCE_LINKED") != nullptr;
+    static const bool two_launch = std::getenv("E2D_TWO_LAUNCH") != nullptr;
+    const bool        linked = nranks > 1 || force_linked;
+    const bool        solo = !linked && !two_launch;
+    SlabState &       hs = *h->h_state;
+    std::memset(&hs, 0, sizeof hs);
     hs.t = h->t;
     hs.dt = h->dt_last;
-    hs.invdt_acc = 0;
     hs.nStep = h->nStep;
     hs.done = !(h->t < p.tEnd && h->nStep < max_steps);
-    hs.pending = 0;
-    hs.error = 0;
     E2D_CUDA(cudaMemcpyAsync(h->d_state, h->h_state, sizeof(SlabState), cudaMemcpyHostToDevice, st));
     {
       const double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
-      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, &h->d_state->invdt_acc, st));
+      // solo: the first step has parity 0 and reads solo_acc[0]
+      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, solo ? &h->d_state->solo_acc[0] : &h->d_state->invdt_acc, st));
     }
 
     SlabStepArgs sa;
@@ -802,6 +838,17 @@ extern "C"
     sa.max_steps = (int)max_steps;
     sa.dt_hist = h->d_hist;
     sa.hist_cap = h->hist_cap;
+    {
+      // how long a kernel may wait for a peer's halo rows / invDt partial before it gives up (seconds of SM clock at
+      // 2 GHz).  Ranks may enter e2d_run at different times (PeerSlabRun.run puts a barrier in front, other callers
+      // should too); 60 s covers first-call initialisation and rank-0-only work in between.
+      static const double timeout_s = [] {
+        const char * e = std::getenv("E2D_PEER_TIMEOUT_S");
+        const double v = e ? std::atof(e) : 60.0;
+        return v > 0.0 ? v : 60.0;
+      }();
+      sa.timeout_clocks = (long long)(timeout_s * 2.0e9);
+    }
     SlabPushArgs pa;
     pa.isize = h->g.isize;
     pa.jsize = h->g.jsize;
@@ -816,11 +863,6 @@ extern "C"
     pa.upper = h->peers.upper;
     const int faces = faces_for(h);
     FusedLink lk{};
-    // E2D_FORCE_LINKED=1 (development aid): run the peer-publishing instantiation of the step kernel on a single
-    // GPU — no neighbours, it only publishes its invDt partial to its own slot — so that it can be timed and profiled
-    // without a second rank
-    static const bool force_linked = std::getenv("E2D_FORCE_LINKED") != nullptr;
-    const bool        linked = nranks > 1 || force_linked;
     if (linked)
     {
       lk.cnt = h->d_comm->fused_cnt;
@@ -833,6 +875,17 @@ extern "C"
       lk.nranks = nranks;
       lk.rank = rank;
     }
+    SoloLoop so;
+    so.st = h->d_state;
+    so.cfl = p.cfl;
+    so.tEnd = p.tEnd;
+    so.max_steps = (int)max_steps;
+    so.dt_hist = h->d_hist;
+    so.hist_cap = h->hist_cap;
+    so.bc_xmin = p.boundary_type_xmin;
+    so.bc_xmax = p.boundary_type_xmax;
+    so.bc_ymin = p.boundary_type_ymin;
+    so.bc_ymax = p.boundary_type_ymax;
 
     E2D_CUDA(cudaEventRecord(h->ev[0], st));
     int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when the step is a no-op
@@ -848,13 +901,19 @@ extern "C"
     // data on every rank and looked at after the same batches, so all ranks stop together.
     // The flags of this call start one past anything an earlier call's last fused step may have published.
     h->seq += 1;
-    // Single GPU, no per-step event records in between: the two kernels of a step are launched as programmatic
+    // Single GPU, no per-step event records in between: consecutive kernels are launched as programmatic
     // dependents of each other, so their launch latency overlaps the predecessor's tail (it matters on small grids,
-    // where a step is tens of microseconds).  Peers: kept off — their kernels spin on remote flags.
+    // where a step is a few microseconds).  Peers: kept off — their kernels spin on remote flags.
     static const bool pdl_off = std::getenv("E2D_NO_PDL") != nullptr;
     const bool        pdl = nranks == 1 && !h->timing && !pdl_off;
     bool first = true;
     bool finished = hs.done != 0;
+    if (solo && !finished)
+    { // the only boundary fill of the call: every later step finds the ghost cells pushed by its predecessor
+      double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
+      E2D_CUDA(launch_make_boundaries(p, h->g, cur, faces, nullptr, st));
+    }
+    long issued = 0; // steps issued by this call: solo parity
     while (!finished)
     {
       long todo = max_steps - n_host;
@@ -865,6 +924,18 @@ extern "C"
         const int which = n_host % 2; // 0: U -> U2
         double *  in = which == 0 ? h->U : h->U2;
         double *  out = which == 0 ? h->U2 : h->U;
+        if (solo)
+        {
+          so.parity = (int)(issued & 1);
+          ++issued;
+          if (h->timing)
+            E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
+          E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, nullptr, &h->d_state->solo_acc[1 - so.parity], nullptr, st,
+                                     nullptr, nullptr, 2, 0, pdl, &so));
+          if (h->timing)
+            E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));
+          continue;
+        }
         h->seq += 1;
         sa.seq = pa.seq = h->seq;
         sa.parity = pa.parity = (int)(h->seq & 1);
@@ -898,7 +969,8 @@ extern "C"
         if (h->timing)
           E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));
       }
-      E2D_CUDA(launch_slab_finish(sa, st)); // closes the last opened step (a no-op for the next batch's first step)
+      if (!solo)
+        E2D_CUDA(launch_slab_finish(sa, st)); // closes the last opened step (a no-op for the next batch's first step)
       E2D_CUDA(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(SlabState), cudaMemcpyDeviceToHost, st));
       E2D_CUDA(cudaStreamSynchronize(st));
       if (h->timing)
@@ -909,7 +981,12 @@ extern "C"
           step_kernel_ms += ms_k;
         }
       if (hs.error)
-        return fail(E2D_ERR_CUDA, "slab loop: timed out waiting for a peer GPU (did a rank die?)");
+      {
+        h->seq_poisoned = true;
+        return fail(E2D_ERR_CUDA,
+                    "slab loop: timed out waiting for a peer GPU (did a rank die, or enter e2d_run much later than the "
+                    "others?); the loop was stopped and the state of this handle is INVALID");
+      }
       finished = hs.done != 0 || n_host >= max_steps;
     }
     E2D_CUDA(cudaEventRecord(h->ev[1], st));
@@ -939,20 +1016,8 @@ extern "C"
   {
     E2D_CUDA(preload_slab_kernels());
     E2D_CUDA(preload_step_kernels());
-    const long cap = (long)h->p.nStepmax + 128;
-    if (h->hist_cap < cap)
-    {
-      double * nh = nullptr;
-      E2D_CUDA(cudaMalloc(&nh, sizeof(double) * cap));
-      E2D_CUDA(cudaMemset(nh, 0, sizeof(double) * cap));
-      if (h->d_hist)
-      {
-        E2D_CUDA(cudaMemcpy(nh, h->d_hist, sizeof(double) * h->hist_cap, cudaMemcpyDeviceToDevice));
-        cudaFree(h->d_hist);
-      }
-      h->d_hist = nh;
-      h->hist_cap = cap;
-    }
+    if (int rc = ensure_history(h, (long)h->p.nStepmax + 128))
+      return rc;
     return E2D_OK;
   }
 
@@ -960,6 +1025,7 @@ extern "C"
   neighbours_of(const e2d_handle * h, int & lower, int & upper)
   {
     const int r = h->slab.rank, n = h->slab.nranks;
+    // e2d_create refuses slabs with only ONE of the two y faces periodic, so both wraps exist or neither does
     lower = r > 0 ? r - 1 : (h->p.boundary_type_ymin == E2D_BC_PERIODIC ? n - 1 : -1);
     upper = r < n - 1 ? r + 1 : (h->p.boundary_type_ymax == E2D_BC_PERIODIC ? 0 : -1);
     if (n == 1)

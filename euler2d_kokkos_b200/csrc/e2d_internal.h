@@ -65,6 +65,25 @@ struct SlabState
   int                done;
   int                pending; // dt of an opened step not yet added to t
   int                error;   // a wait for a peer timed out
+  // single-GPU loop folded into the step kernel (SoloLoop): invDt accumulators by step parity, arrival counter
+  unsigned long long solo_acc[2];
+  unsigned int       solo_cnt;
+};
+
+// Single-GPU device-resident loop with ONE launch per step: the step kernel itself opens the step (every block
+// derives dt = cfl / invDt and the tEnd clamp from device memory: src/HydroRun.h:246, src/main.cpp:100,131-134),
+// pushes the boundary fill of the state it has just produced into that array's ghost cells (what make_boundaries
+// would do at the start of the next step, e2d_bc.cuh), and its last block closes the step (t += dt, nStep++, dt
+// history: main.cpp:142-143).
+struct SoloLoop
+{
+  SlabState * st = nullptr;
+  double      cfl = 0.0, tEnd = 0.0;
+  int         max_steps = 0;
+  int         parity = 0; // the step reads solo_acc[parity], accumulates the next invDt into solo_acc[1 - parity]
+  double *    dt_hist = nullptr;
+  long        hist_cap = 0;
+  int         bc_xmin = 0, bc_xmax = 0, bc_ymin = 0, bc_ymax = 0;
 };
 
 struct SlabPushArgs
@@ -91,6 +110,7 @@ struct SlabStepArgs
   int                max_steps;
   double *           dt_hist;
   long               hist_cap;
+  long long          timeout_clocks = 120000000000ll; // bound of a wait for a peer, in SM clocks (e2d_run sets it)
 };
 
 cudaError_t launch_slab_push(const SlabPushArgs & a, cudaStream_t st);
@@ -135,7 +155,12 @@ cudaError_t launch_fused_step(const e2d_params & p, const Geom & g, const double
                               const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done,
                               cudaStream_t st, const MarchPeers * peers = nullptr, FusedLink * link = nullptr,
                               int j_first = 2, int j_last = 0 /* <= 0: all rows; else rows [j_first, j_last) */,
-                              bool pdl = false /* see launch_slab_boundaries */);
+                              bool pdl = false /* see launch_slab_boundaries */,
+                              const SoloLoop * solo = nullptr /* single-GPU loop: dt, invDt, done come from solo->st */);
+int         device_sm_count(); // multiprocessors of the current device (cached per device)
+// refined reciprocal of the strict division sequence for denominator d (device-evaluated once per value, cached;
+// synchronises on a miss — e2d_create warms it for dx, dy so that no launch inside a loop ever misses)
+double      refined_reciprocal(double d);
 
 // Programmatic dependent launch (sm_90+).  Both are no-ops in a kernel launched without the attribute.
 #if defined(__CUDACC__)

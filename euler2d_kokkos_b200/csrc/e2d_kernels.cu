@@ -3,8 +3,13 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (strict: bit parity with the
 // reference's FMA-free x86 build).  Data layout: SoA planes, off = i + isize*(j + jsize*var);
 // threadIdx.x always walks i, so every global access of a warp is a contiguous 256-byte run.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "e2d_bc.cuh"
 #include "e2d_internal.h"
@@ -16,8 +21,14 @@ namespace e2d
 namespace
 {
 
-constexpr int kBX = 128;       // threads per block of the marching kernel (= columns incl. 4 halo columns)
-constexpr int kMarchMinBlocks = 3; // blocks of 128 threads per SM (<= 168 registers per thread)
+#ifndef E2D_BX
+#  define E2D_BX 128
+#endif
+#ifndef E2D_STRICT_MIN_BLOCKS
+#  define E2D_STRICT_MIN_BLOCKS (384 / E2D_BX)
+#endif
+constexpr int kBX = E2D_BX;    // threads per block of the marching kernel (= columns incl. 4 halo columns)
+constexpr int kMarchMinBlocks = E2D_STRICT_MIN_BLOCKS; // 384 threads per SM (<= 168 registers per thread)
 #ifndef E2D_FAST_MIN_BLOCKS
 #  define E2D_FAST_MIN_BLOCKS 4
 #endif
@@ -32,6 +43,13 @@ constexpr int
 march_min_blocks(int math)
 {
   return math == 1 ? kMarchMinBlocksFast : kMarchMinBlocks;
+}
+
+// row handled by a block of a grid_rows() launch: gridDim.y is capped at 32768 rows, gridDim.z carries the rest
+__device__ __forceinline__ int
+grid_row()
+{
+  return (int)(blockIdx.y + blockIdx.z * gridDim.y);
 }
 
 __host__ __device__ __forceinline__ size_t
@@ -80,7 +98,7 @@ __global__ void __launch_bounds__(128)
 k_init_problem(Geom g, InitArgs a, double * __restrict__ U, unsigned long long * __restrict__ n_inside)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
+  const int j = grid_row();
   if (i >= g.isize || j >= g.jsize)
     return;
   const int    gw = 2;
@@ -295,8 +313,8 @@ __global__ void __launch_bounds__(256)
 k_convert_to_primitives(Geom g, Settings s, const double * __restrict__ U, double * __restrict__ Q)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
-  if (i >= g.isize)
+  const int j = grid_row();
+  if (i >= g.isize || j >= g.jsize)
     return;
   double u[4], q[4];
   load4(U, g, i, j, u);
@@ -328,7 +346,7 @@ k_compute_and_store_fluxes(Geom g, Settings s, const double * __restrict__ Q, do
                            double * __restrict__ Fy, double dtdx, double dtdy)
 {
   const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = 2 + blockIdx.y;
+  const int j = 2 + grid_row();
   if (i > g.isize - 2 || j > g.jsize - 2)
     return;
   double q[4], dqX[4], dqY[4], s0[4], qn[4], dqXn[4], dqYn[4], s0n[4], ql[4], qr[4], f[4];
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(256)
 k_update(Geom g, double * __restrict__ U, const double * __restrict__ Fx, const double * __restrict__ Fy)
 {
   const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = 2 + blockIdx.y;
+  const int j = 2 + grid_row();
   if (i >= g.isize - 2 || j >= g.jsize - 2)
     return;
   const size_t plane = (size_t)g.isize * g.jsize;
@@ -393,7 +411,7 @@ k_compute_slopes(Geom g, Settings s, const double * __restrict__ Q, double * __r
                  double * __restrict__ Sy)
 {
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = 1 + blockIdx.y;
+  const int j = 1 + grid_row();
   if (i > g.isize - 2 || j > g.jsize - 2)
     return;
   double q[4], dqX[4], dqY[4];
@@ -408,7 +426,7 @@ k_trace_and_fluxes(Geom g, Settings s, const double * __restrict__ Q, const doub
                    const double * __restrict__ Sy, double * __restrict__ F, double dtdx, double dtdy)
 {
   const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = 2 + blockIdx.y;
+  const int j = 2 + grid_row();
   if (i > g.isize - 2 || j > g.jsize - 2)
     return;
   const int in = DIR == 1 ? i - 1 : i, jn = DIR == 1 ? j : j - 1;
@@ -452,7 +470,7 @@ __global__ void __launch_bounds__(256)
 k_update_dir(Geom g, double * __restrict__ U, const double * __restrict__ F)
 {
   const int i = 2 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = 2 + blockIdx.y;
+  const int j = 2 + grid_row();
   if (i >= g.isize - 2 || j >= g.jsize - 2)
     return;
   const size_t plane = (size_t)g.isize * g.jsize;
@@ -480,9 +498,34 @@ st_release_sys_u64(unsigned long long * p, unsigned long long v)
 // Epilogue of the peer-publishing instantiation (multi-GPU, e2d_slab.cu).  Kept out of line: inlined, its live
 // values and addressing leak into the register allocation of the marching loop (ncu: +17 register moves per row and
 // 4 % of the fast kernel's throughput).
-__device__ __noinline__ void
-publish_to_peers(const MarchArgs & a, const FusedLink & link, bool active, int i, int j0, int j1, bool store)
+// the rows [j0, j1) and the column a thread of this block owns, recomputed from the block indices: the epilogues take
+// nothing from the marching loop's registers (values kept alive for them cost the loop a spill and three S2Rs)
+template <int BX, int LOOP>
+__device__ __forceinline__ bool
+block_rows(const MarchArgs & a, int & j0, int & j1)
 {
+  int seg = blockIdx.y;
+  if (LOOP == 1)
+  {
+    const int nseg = gridDim.y;
+    seg = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? nseg - 1 : (int)blockIdx.y - 1);
+  }
+  const int j_end = a.j_last > 0 ? a.j_last : a.jsize - 2;
+  j0 = a.j_first + seg * a.seg_rows;
+  j1 = j0 + a.seg_rows;
+  if (j1 > j_end)
+    j1 = j_end;
+  return j0 < j1;
+}
+
+template <int BX>
+__device__ __noinline__ void
+publish_to_peers(const MarchArgs & a, const FusedLink & link)
+{
+  int        j0, j1;
+  const bool active = block_rows<BX, 1>(a, j0, j1);
+  const int  t = threadIdx.x, i = blockIdx.x * (BX - 4) + t;
+  const bool store = (t >= 2) && (t <= BX - 3) && (i >= 2) && (i <= a.isize - 3);
   const bool lo = active && a.peer_lo && j0 <= 3 && j1 > 2;
   const bool hi = active && a.peer_hi && j0 <= a.jsize - 3 && j1 > a.jsize - 4;
   // Edge segments: every thread copies the edge rows of ITS column (which it stored itself a moment ago: program
@@ -547,27 +590,146 @@ publish_to_peers(const MarchArgs & a, const FusedLink & link, bool active, int i
   }
 }
 
-template <int SOLVER, bool FUSE_DT, bool LINKED, int MATH = 0>
+// Epilogue of the single-GPU loop instantiation (SoloLoop, e2d_internal.h).  Out of line for the same reason.
+//  1. Boundary push: every ghost cell whose SOURCE cell (e2d_bc.cuh: bc_map) this block has just produced is written
+//     now, into the output array — the fill HydroRun::make_boundaries would do at the start of the next step
+//     (src/HydroRun.h:296, :390-399), same composed index maps, same signs, bit for bit.  Only blocks that hold one of
+//     the columns {2, 3, nx, nx+1} or rows {2, 3, ny, ny+1} have anything to do.
+//  2. The last block to arrive closes the step: t += dt, nStep++, dt history, loop condition (main.cpp:100,142-143),
+//     and clears the invDt accumulator the NEXT-but-one step will fill.
+// dt of the step a SoloLoop launch performs, from the device-resident scalars (HydroRun.h:246, main.cpp:131-134)
+__device__ __forceinline__ double
+solo_dt(const SoloLoop & solo, double t)
+{
+  const double invDt = __longlong_as_double((long long)solo.st->solo_acc[solo.parity]);
+  double       dt = solo.cfl / invDt;
+  if (t + dt > solo.tEnd)
+    dt = solo.tEnd - t;
+  return dt;
+}
+
+template <int BX>
+__device__ __noinline__ void
+solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
+{
+  int        j0, j1;
+  const bool active = block_rows<BX, 2>(a, j0, j1);
+  const int  bx = blockIdx.x;
+  __syncthreads(); // this block's stores to Uout are visible to all its threads
+  if (active)
+  {
+    Geom g;
+    g.isize = a.isize;
+    g.jsize = a.jsize;
+    g.nx = a.isize - 4;
+    g.ny = a.jsize - 4;
+    g.j_off = 0;
+    BcArgs bc;
+    bc.bc_xmin = solo.bc_xmin;
+    bc.bc_xmax = solo.bc_xmax;
+    bc.bc_ymin = solo.bc_ymin;
+    bc.bc_ymax = solo.bc_ymax;
+    bc.faces = E2D_FACES_ALL;
+    const int    nx = g.nx, ny = g.ny;
+    const int    I0 = bx * (BX - 4) + 2;                                   // produced columns [I0, I1)
+    const int    I1 = (I0 + BX - 4 < a.isize - 2) ? I0 + BX - 4 : a.isize - 2;
+    const size_t plane = (size_t)a.isize * a.jsize;
+    const bool   col_src = (I0 <= 3) || (I1 > nx); // holds a column of {2, 3, nx, nx+1}
+    const bool   row_src = (j0 <= 3) || (j1 > ny); // holds a row of {2, 3, ny, ny+1}
+    if (col_src)
+    { // x-ghost columns of the rows [j0, j1)
+      const int n = 4 * (j1 - j0);
+      for (int k = threadIdx.x; k < n; k += BX)
+      {
+        const int gsel = k & 3, j = j0 + (k >> 2);
+        const int i = gsel < 2 ? gsel : nx + gsel;
+        int       i0, jj0;
+        bool      in_x, in_y, flip_u, flip_v;
+        bc_map(g, bc, i, j, i0, jj0, in_x, in_y, flip_u, flip_v);
+        if (i0 < I0 || i0 >= I1)
+          continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          a.Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
+            bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+      }
+    }
+    if (row_src)
+    { // y-ghost rows: this block's own columns and the four x-ghost columns (corners)
+      const int own = I1 - I0, ncols = own + 4, n = 4 * ncols;
+      for (int k = threadIdx.x; k < n; k += BX)
+      {
+        const int gsel = k / ncols, c = k - gsel * ncols;
+        const int j = gsel < 2 ? gsel : ny + gsel;
+        const int i = c < own ? I0 + c : ((c - own) < 2 ? (c - own) : nx + (c - own));
+        int       i0, jj0;
+        bool      in_x, in_y, flip_u, flip_v;
+        bc_map(g, bc, i, j, i0, jj0, in_x, in_y, flip_u, flip_v);
+        if (i0 < I0 || i0 >= I1 || jj0 < j0 || jj0 >= j1)
+          continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          a.Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
+            bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+      }
+    }
+  }
+  __threadfence(); // this block's atomicMax (and ghost cells) before its arrival count
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    SlabState * st = solo.st;
+    if (atomicAdd(&st->solo_cnt, 1u) == gridDim.x * gridDim.y - 1)
+    {
+      st->solo_cnt = 0;
+      __threadfence();
+      const int    n = st->nStep;
+      const double dt = solo_dt(solo, st->t); // the value every block derived at the start of this launch
+      if (solo.dt_hist && n < solo.hist_cap)
+        solo.dt_hist[n] = dt;
+      const double t = st->t + dt; // main.cpp:142-143
+      st->t = t;
+      st->dt = dt;
+      st->nStep = n + 1;
+      st->done = !(t < solo.tEnd && n + 1 < solo.max_steps); // main.cpp:100
+      st->solo_acc[solo.parity] = 0ull; // consumed by every block of this step; refilled by the next step
+    }
+  }
+}
+
+// LOOP: 0 = one step, dt from the arguments;  1 = multi-GPU slab loop (publishes halo rows + invDt partial to the
+// peers, e2d_slab.cu);  2 = single-GPU loop with one launch per step (SoloLoop: dt, boundary push, bookkeeping).
+template <int SOLVER, bool FUSE_DT, int LOOP, int MATH = 0, bool TYP = false>
 __global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
 k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_done,
-             const __grid_constant__ FusedLink link)
+             const __grid_constant__ FusedLink link, const __grid_constant__ SoloLoop solo)
 {
   pdl_wait_for_predecessor(); // (no-ops unless launched with the programmatic-serialization attribute)
   pdl_release_successor();
   if (d_done && *d_done)
     return;
+  double dt = a.d_dt ? *a.d_dt : a.dt;
+  if (LOOP == 2)
+  { // open the step: every thread derives the same dt from the same device-resident scalars (HydroRun.h:246,
+    // main.cpp:100,131-134); they were written by the last block of the previous launch
+    const SlabState * st = solo.st;
+    const double      t = st->t;
+    if (!(t < solo.tEnd && st->nStep < solo.max_steps))
+      return;
+    dt = solo_dt(solo, t);
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MarchSmem<kBX> &                  sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
-  MarchThread<kBX, SOLVER, FUSE_DT, MATH> th;
+  MarchThread<kBX, SOLVER, FUSE_DT, MATH, TYP> th;
   // blockIdx.y -> row segment: with peers the two EDGE segments come first, so that the halo rows are on their way
   // (and usually landed) while the interior is still being computed
   int seg = blockIdx.y;
-  if (LINKED)
+  if (LOOP == 1)
   {
     const int nseg = gridDim.y;
     seg = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? nseg - 1 : (int)blockIdx.y - 1);
   }
-  const bool active = th.init(a, sm, threadIdx.x, blockIdx.x, seg);
+  const bool active = th.init(a, sm, threadIdx.x, blockIdx.x, seg, dt);
   if (active)
   {
     __syncthreads();
@@ -582,8 +744,10 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
     if (FUSE_DT && a.invdt_bits)
       block_max_to_global(th.invdt, a.invdt_bits);
   }
-  if (LINKED)
-    publish_to_peers(a, link, active, th.i, th.j0, th.j1, th.store);
+  if (LOOP == 1)
+    publish_to_peers<kBX>(a, link);
+  if (LOOP == 2)
+    solo_epilogue<kBX>(a, solo);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -880,10 +1044,13 @@ solver_for(const e2d_params & p)
   return p.honourRiemannSolver ? p.riemannSolverType : E2D_RIEMANN_HLLC;
 }
 
+// one block row per grid row; gridDim.y may not exceed 65535, so tall slabs spill into gridDim.z (grid_row())
 static inline dim3
 grid_rows(int ncols, int nrows, int block)
 {
-  return dim3((unsigned)((ncols + block - 1) / block), (unsigned)nrows, 1);
+  const int ycap = 32768;
+  const int ny = nrows < ycap ? nrows : ycap;
+  return dim3((unsigned)((ncols + block - 1) / block), (unsigned)(ny < 1 ? 1 : ny), (unsigned)((nrows + ycap - 1) / ycap > 0 ? (nrows + ycap - 1) / ycap : 1));
 }
 
 cudaError_t
@@ -982,7 +1149,7 @@ launch_reduce_invdt(const e2d_params & p, const Geom & g, const double * U, unsi
   const int bx = (g.nx + 255) / 256;
   int       by = g.ny < 1 ? 1 : g.ny;
   // enough blocks to fill the machine, few enough that the atomics stay negligible
-  const int max_by = (148 * 8 + bx - 1) / bx;
+  const int max_by = (device_sm_count() * 8 + bx - 1) / bx;
   if (by > max_by)
     by = max_by;
   k_reduce_invdt<<<dim3(bx < 1 ? 1 : bx, by), 256, 0, st>>>(g, make_settings(p), U, d_bits);
@@ -1078,14 +1245,69 @@ launch_update_dir(const e2d_params &, const Geom & g, double * U, const double *
   return cudaGetLastError();
 }
 
+// The refined reciprocal the strict division sequence uses for a denominator (e2d_lean.cuh: recip_of), evaluated on
+// the device once per distinct value and cached: dx and dy enter the CFL integrand of every cell, and as kernel
+// arguments they cost no registers.  NaN on failure: the fast-path guards then reject and the plain operators run.
+namespace
+{
+__global__ void
+k_refined_reciprocal(double d, double * out)
+{
+  bool ok = true;
+  *out = recip_of<true, false>(d, ok).y;
+}
+} // namespace
+
+double
+refined_reciprocal(double d)
+{
+  static std::mutex                             mu;
+  static std::vector<std::pair<double, double>> cache;
+  std::lock_guard<std::mutex>                   lock(mu);
+  for (const auto & e : cache)
+    if (e.first == d)
+      return e.second;
+  double   y = std::numeric_limits<double>::quiet_NaN();
+  double * dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(double)) == cudaSuccess)
+  {
+    k_refined_reciprocal<<<1, 1>>>(d, dev);
+    count_launch();
+    if (cudaMemcpy(&y, dev, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      y = std::numeric_limits<double>::quiet_NaN();
+    cudaFree(dev);
+  }
+  if (y == y)
+    cache.emplace_back(d, y);
+  return y;
+}
+
+// multiprocessors of the current device (148 on a B200), cached per device
+int
+device_sm_count()
+{
+  static std::atomic<int> cached[64] = {};
+  int                     dev = 0;
+  cudaGetDevice(&dev);
+  int n = cached[dev & 63].load(std::memory_order_relaxed);
+  if (n <= 0)
+  {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev & 63].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 // Rows per block segment.  Every segment re-traces 2 rows and re-converts 3, so segments should be long; but
-// the grid (nbx column blocks x nseg segments) should also fill the 148 SMs x blocks_per_sm resident slots in
+// the grid (nbx column blocks x nseg segments) should also fill the SMs x blocks_per_sm resident slots in
 // an integral number of equal waves, because a block lives for a whole segment.  Pick the segment count that
-// minimises  waves x (rows per segment + per-segment overhead).
+// minimises  waves x (rows per segment + per-segment overhead).  Grids of less than one wave get segments as short
+// as two rows: the step is then a latency chain of (rows + overhead) row-times, not a throughput problem.
 static int
 choose_seg_rows(int nbx, int ny, int blocks_per_sm)
 {
-  const int  slots = 148 * blocks_per_sm;
+  const int  slots = device_sm_count() * blocks_per_sm;
   const int  overhead_rows = 4;
   long       best_cost = -1;
   int        best_rows = ny;
@@ -1102,16 +1324,76 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
       best_cost = cost;
       best_rows = rows;
     }
-    if (rows <= 8)
+    if (rows <= 2)
       break;
   }
   return best_rows < 1 ? 1 : best_rows;
 }
 
+namespace
+{
+// one-time, per device, per instantiation: opt in to the dynamic shared memory the kernel needs
+template <typename K>
+cudaError_t
+configure_once(K kernel, size_t smem, std::atomic<unsigned long long> & done_mask)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask.load(std::memory_order_acquire) & bit)
+    return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    done_mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
+template <int SOL, bool FUSE, int LOOP, int MATH, bool TYP>
+cudaError_t
+launch_instance(const dim3 & grid, size_t smem, cudaStream_t st, bool pdl, const MarchArgs & a, const int * d_done,
+                const FusedLink & lk, const SoloLoop & so)
+{
+  static std::atomic<unsigned long long> configured{ 0 };
+  auto                                   kernel = k_fused_step<SOL, FUSE, LOOP, MATH, TYP>;
+  if (cudaError_t e = configure_once(kernel, smem, configured))
+    return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kBX);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, a, d_done, lk, so);
+}
+
+// mode: 0 plain without the fused CFL reduction, 1 plain with it, 2 peers (multi-GPU loop), 3 solo (single-GPU loop)
+template <int SOL, int MATH, bool TYP>
+cudaError_t
+launch_mode(int mode, const dim3 & grid, size_t smem, cudaStream_t st, bool pdl, const MarchArgs & a,
+            const int * d_done, const FusedLink & lk, const SoloLoop & so)
+{
+  switch (mode)
+  {
+    case 0:
+      return launch_instance<SOL, false, 0, MATH, TYP>(grid, smem, st, pdl, a, d_done, lk, so);
+    case 1:
+      return launch_instance<SOL, true, 0, MATH, TYP>(grid, smem, st, pdl, a, d_done, lk, so);
+    case 2:
+      return launch_instance<SOL, true, 1, MATH, TYP>(grid, smem, st, pdl, a, d_done, lk, so);
+    default:
+      return launch_instance<SOL, true, 2, MATH, TYP>(grid, smem, st, pdl, a, d_done, lk, so);
+  }
+}
+} // namespace
+
 cudaError_t
 launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, double * Uout, double dt,
                   const double * d_dt, unsigned long long * d_invdt_bits, const int * d_done, cudaStream_t st,
-                  const MarchPeers * peers, FusedLink * link, int j_first, int j_last, bool pdl)
+                  const MarchPeers * peers, FusedLink * link, int j_first, int j_last, bool pdl, const SoloLoop * solo)
 {
   MarchArgs a;
   a.Uin = Uin;
@@ -1123,12 +1405,15 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   a.dt = dt;
   a.d_dt = d_dt;
   a.invdt_bits = d_invdt_bits;
+  const bool fast_arith = p.arithmetic == E2D_ARITH_FAST && solver_for(p) == E2D_RIEMANN_HLLC;
+  a.rdx_y = fast_arith ? 1.0 / a.s.dx : refined_reciprocal(a.s.dx);
+  a.rdy_y = fast_arith ? 1.0 / a.s.dy : refined_reciprocal(a.s.dy);
   const int nbx = (g.nx + (kBX - 4) - 1) / (kBX - 4);
   // rows [j_first, j_last) only (host-streamed step); default: the whole slab
   const int rows = j_last > 0 ? j_last - j_first : g.ny;
   if (j_last > 0)
   {
-    if (link || j_first < 2 || j_last > g.jsize - 2 || rows < 1)
+    if (link || solo || j_first < 2 || j_last > g.jsize - 2 || rows < 1)
       return cudaErrorInvalidValue;
     a.j_first = j_first;
     a.j_last = j_last;
@@ -1141,9 +1426,11 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
   const bool fuse = d_invdt_bits != nullptr;
   FusedLink  lk{};
+  SoloLoop   so{};
+  int        mode = fuse ? 1 : 0;
   if (link)
   {
-    if (!fuse || !peers)
+    if (!fuse || !peers || solo)
       return cudaErrorInvalidValue;
     a.peer_lo = peers->lo;
     a.peer_hi = peers->hi;
@@ -1154,56 +1441,29 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     link->n_hi = (unsigned)nbx * (((g.ny - 2) / a.seg_rows != (g.ny - 1) / a.seg_rows) ? 2u : 1u);
     link->n_all = (unsigned)nbx * (unsigned)nseg;
     lk = *link;
+    mode = 2;
   }
+  if (solo)
+  {
+    if (!fuse || !solo->st)
+      return cudaErrorInvalidValue;
+    so = *solo;
+    mode = 3;
+  }
+  // the common case as its own instantiation (HLLC, strict): limited slopes on square cells (MarchThread<.., TYP>)
+  const bool   typ = a.c.limited && p.dx == p.dy;
   const size_t smem = sizeof(MarchSmem<kBX>);
-  cudaError_t launch_err = cudaSuccess;
-#define E2D_FS1(SOL, FUSE, LINKED, MATH)                                                                     \
-  do                                                                                                      \
-  {                                                                                                       \
-    static bool configured_on[64] = {}; /* per instantiation and device; benign race: idempotent */      \
-    int         dev_ = 0;                                                                                 \
-    cudaGetDevice(&dev_);                                                                                 \
-    bool & configured = configured_on[dev_ & 63];                                                         \
-    if (!configured)                                                                                      \
-    {                                                                                                     \
-      cudaError_t e = cudaFuncSetAttribute(k_fused_step<SOL, FUSE, LINKED, MATH>,                         \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-      if (e != cudaSuccess)                                                                               \
-        return e;                                                                                         \
-      configured = true;                                                                                  \
-    }                                                                                                     \
-    cudaLaunchConfig_t cfg_ = {};                                                                         \
-    cfg_.gridDim = grid;                                                                                  \
-    cfg_.blockDim = dim3(kBX);                                                                            \
-    cfg_.dynamicSmemBytes = smem;                                                                         \
-    cfg_.stream = st;                                                                                     \
-    cudaLaunchAttribute at_[1];                                                                           \
-    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
-    at_[0].val.programmaticStreamSerializationAllowed = 1;                                                \
-    cfg_.attrs = at_;                                                                                     \
-    cfg_.numAttrs = pdl ? 1 : 0;                                                                          \
-    launch_err = cudaLaunchKernelEx(&cfg_, k_fused_step<SOL, FUSE, LINKED, MATH>, a, d_done, lk);         \
-  } while (0)
-#define E2D_FS(SOL, MATH)               \
-  do                                    \
-  {                                     \
-    if (link)                           \
-      E2D_FS1(SOL, true, true, MATH);   \
-    else if (fuse)                      \
-      E2D_FS1(SOL, true, false, MATH);  \
-    else                                \
-      E2D_FS1(SOL, false, false, MATH); \
-  } while (0)
-  if (sol == 0)
-    E2D_FS(0, 0);
-  else if (sol == 1)
-    E2D_FS(1, 0);
+  cudaError_t  launch_err;
+  if (sol == E2D_RIEMANN_APPROX)
+    launch_err = launch_mode<0, 0, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (sol == E2D_RIEMANN_HLL)
+    launch_err = launch_mode<1, 0, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (fastm)
-    E2D_FS(2, 1);
+    launch_err = launch_mode<2, 1, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (typ)
+    launch_err = launch_mode<2, 0, true>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else
-    E2D_FS(2, 0);
-#undef E2D_FS
-#undef E2D_FS1
+    launch_err = launch_mode<2, 0, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   count_launch();
   return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
 }
@@ -1213,23 +1473,21 @@ preload_step_kernels()
 {
   cudaFuncAttributes fa;
   cudaError_t        e = cudaFuncGetAttributes(&fa, k_reduce_invdt);
-#define E2D_PRE(SOL)                                                      \
-  if (e == cudaSuccess)                                                   \
-    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, true>);        \
-  if (e == cudaSuccess)                                                   \
-    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, false>);       \
-  if (e == cudaSuccess)                                                   \
-    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, false, false>);
-  E2D_PRE(0)
-  E2D_PRE(1)
-  E2D_PRE(2)
+#define E2D_PRE(SOL, MATH, TYP)                                                 \
+  if (e == cudaSuccess)                                                         \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, 1, MATH, TYP>);      \
+  if (e == cudaSuccess)                                                         \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, 2, MATH, TYP>);      \
+  if (e == cudaSuccess)                                                         \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, 0, MATH, TYP>);      \
+  if (e == cudaSuccess)                                                         \
+    e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, false, 0, MATH, TYP>);
+  E2D_PRE(0, 0, false)
+  E2D_PRE(1, 0, false)
+  E2D_PRE(2, 0, false)
+  E2D_PRE(2, 0, true)
+  E2D_PRE(2, 1, false)
 #undef E2D_PRE
-  if (e == cudaSuccess)
-    e = cudaFuncGetAttributes(&fa, k_fused_step<2, true, true, 1>);
-  if (e == cudaSuccess)
-    e = cudaFuncGetAttributes(&fa, k_fused_step<2, true, false, 1>);
-  if (e == cudaSuccess)
-    e = cudaFuncGetAttributes(&fa, k_fused_step<2, false, false, 1>);
   return e;
 }
 

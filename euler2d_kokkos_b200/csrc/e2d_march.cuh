@@ -61,6 +61,7 @@ struct MarchArgs
   int                  j_last = 0;   // host-streamed step (e2d_capi.cu) advance chunk by chunk as the rows arrive
   Settings             s;
   StepConsts           c;
+  double               rdx_y = 0.0, rdy_y = 0.0; // reciprocals of dx, dy for the CFL integrand (MarchThread::recip_dx)
   double               dt;         // used when d_dt == nullptr
   const double *       d_dt;       // device-resident dt (optional)
   unsigned long long * invdt_bits; // optional: atomicMax target for the next step's CFL reduction
@@ -159,10 +160,14 @@ st4(Pair (&row)[2][BX], int t, const double v[4])
 // reciprocal-multiply division, within north_star's 1e-12 of the reference; `[other] arithmetic=fast`).  With
 // MATH == 1 the RY ring holds the fast reciprocal of the density, FX / fyP carry UNSCALED fluxes (the update applies
 // dt/dx, dt/dy inside its fma chain) and the solver is the fast HLLC when SOLVER == 2.
-template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0>
+// TYP: the common case known at compile time — limited slopes (slope_type 1 or 2) on square cells (dx == dy, hence
+// dt/dx == dt/dy): every deck of the reference.  The generic instantiation tests both at run time, which costs the
+// strict kernel ~40 issue slots per row (predicated multiplies, selects against zero slopes, two DSETPs).
+template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0, bool TYP = false>
 struct MarchThread
 {
   static constexpr bool PACK = (MATH == 1); // shared-memory rows as 16-byte pairs
+  static constexpr bool UNFL = E2D_WINDOW_GUARDS != 0; // face densities left unfloored (e2d_lean.cuh)
   // geometry
   int    t, tm, tp; // lane in the block, clamped west / east lanes
   int    i, ic;     // grid column, clamped grid column
@@ -170,7 +175,6 @@ struct MarchThread
   bool   store;     // this thread owns an output column
   size_t plane;     // isize * jsize
   double dtdx, dtdy;
-  Recip  rdx, rdy; // dx, dy and their refined reciprocals (CFL integrand); MATH == 1: .y = 1.0 / dx, 1.0 / dy
   double hdtdx, hdtdy; // MATH == 1: dt/dx/2, dt/dy/2
   int    m3;       // (row being traced) % 3
   // carried across the barrier / rows
@@ -179,6 +183,25 @@ struct MarchThread
   double pend[4];          // U(r-1) + Fx(i, r-1)
   double unD[4];           // updated state of the row completed by the previous phase B (CFL integrand deferred)
   double invdt;
+
+  // dx, dy with their reciprocals for the CFL integrand: kernel arguments (constant bank), no registers.  Strict: the
+  // refined reciprocal of the division sequence (MarchArgs::rdx_y, computed once on the device); fast: 1.0 / dx.
+  E2D_HD static Recip
+  recip_dx(const MarchArgs & a)
+  {
+    Recip r;
+    r.d = a.s.dx;
+    r.y = a.rdx_y;
+    return r;
+  }
+  E2D_HD static Recip
+  recip_dy(const MarchArgs & a)
+  {
+    Recip r;
+    r.d = TYP ? a.s.dx : a.s.dy;
+    r.y = TYP ? a.rdx_y : a.rdy_y;
+    return r;
+  }
 
   E2D_HD void
   load_row(const MarchArgs & a, int j, double u[4]) const
@@ -230,7 +253,7 @@ struct MarchThread
       fast::prim(a.s, a.c, u, q, rd.y);
     else
     {
-      bool ok = true;
+      bool ok = a.c.lean_ok != 0;
       prim_lean<true>(a.s, a.c, u, q, rd, ok);
       if (!ok)
       {
@@ -244,7 +267,7 @@ struct MarchThread
 
   // returns false when the block has no rows to produce (uniform over the block)
   E2D_HD bool
-  init(const MarchArgs & a, MarchSmem<BX> & sm, int lane, int bx, int seg)
+  init(const MarchArgs & a, MarchSmem<BX> & sm, int lane, int bx, int seg, double dt)
   {
     t = lane;
     tm = t > 0 ? t - 1 : 0;
@@ -260,17 +283,8 @@ struct MarchThread
       j1 = j_end;
     if (j0 >= j1)
       return false;
-    const double dt = a.d_dt ? *a.d_dt : a.dt;
     dtdx = dt / a.s.dx; // HydroRun.h:290-291
     dtdy = dt / a.s.dy;
-    bool unused = true;
-    rdx = recip_of<true, false>(a.s.dx, unused);
-    rdy = recip_of<true, false>(a.s.dy, unused);
-    if (MATH == 1)
-    {
-      rdx.y = 1.0 / a.s.dx;
-      rdy.y = 1.0 / a.s.dy;
-    }
     hdtdx = 0.5 * dtdx;
     hdtdy = 0.5 * dtdy;
     invdt = 0.0;
@@ -318,7 +332,7 @@ struct MarchThread
     rd.y = sm.RY[sC][t];
 
     // slope_unsplit_hydro_2d (src/HydroBaseFunctor.h:473-516): slope_type outside {1,2} -> zero slopes
-    const bool limited = (s.slope_type == 1.0) || (s.slope_type == 2.0);
+    const bool limited = TYP || a.c.limited != 0;
     if (MATH == 1)
     {
       const double st0 = limited ? s.slope_type : 0.0;
@@ -328,14 +342,14 @@ struct MarchThread
     }
     else
     {
-      slopes_lean(s.slope_type, limited, qC, qE, qW, dqX);
-      slopes_lean(s.slope_type, limited, qC, qN, qS, dqY);
+      slopes_lean<TYP>(s.slope_type, limited, qC, qE, qW, dqX);
+      slopes_lean<TYP>(s.slope_type, limited, qC, qN, qS, dqY);
 
-      bool ok = true;
+      bool ok = a.c.lean_ok != 0;
       trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
       if (!ok)
         trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
-      trace_faces_lean(s, qC, dqX, dqY, s0, dtdx, dtdy, xmin, xmax, ymin, ymax);
+      trace_faces_lean<TYP, UNFL>(s, qC, dqX, dqY, s0, dtdx, TYP ? dtdx : dtdy, xmin, xmax, ymin, ymax);
     }
 
     st4<PACK>(sm.XMAX[r & 1], t, xmax);
@@ -372,7 +386,7 @@ struct MarchThread
     for (int v = 0; v < 4; ++v)
     {
       fx[v] = fx[v] * dtdx;
-      fy[v] = fy[v] * dtdy;
+      fy[v] = fy[v] * (TYP ? dtdx : dtdy);
     }
     // complete row r-1: UpdateFunctor order (HydroRunFunctors.h:695-713)
     E2D_UNROLL
@@ -396,7 +410,7 @@ struct MarchThread
         u2[1][v] = uP[v];
       }
       prim_lean_multi<LEAN, 2>(s, a.c, u2, q2, rd2, ok);
-      cflv = cfl_tail_lean<LEAN>(s, rdx, rdy, q2[0], rd2[0], ok);
+      cflv = cfl_tail_lean<LEAN>(s, recip_dx(a), recip_dy(a), q2[0], rd2[0], ok);
       E2D_UNROLL
       for (int v = 0; v < 4; ++v)
         qP[v] = q2[1][v];
@@ -448,7 +462,7 @@ struct MarchThread
     {
       double qD[4], ryD;
       fast::prim(s, a.c, unD, qD, ryD);
-      cflv = fast::cfl_tail(s, rdx.y, rdy.y, qD, ryD);
+      cflv = fast::cfl_tail(s, a.rdx_y, a.rdy_y, qD, ryD);
     }
     fast::prim(s, a.c, uP, qP, ryP);
   }
@@ -471,7 +485,7 @@ struct MarchThread
       compute_B_fast(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv);
     else
     {
-      bool ok = true;
+      bool ok = a.c.lean_ok != 0;
       compute_B<true>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
       if (!ok)
         compute_B<false>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
@@ -482,8 +496,10 @@ struct MarchThread
     sm.RY[sS][t] = ryP;
 
     // the CFL integrand just computed belongs to row r-2 (completed by the previous phase B)
-    if (FUSE_DT && store && r >= j0 + 2)
-      invdt = fmax(invdt, cflv); // fmax drops a NaN operand like the reference's reduction (:72)
+    // invDt = fmax(invDt, v) (HydroRunFunctors.h:72) as compare + select: a NaN v compares false and is dropped like
+    // fmax drops it, and the running maximum itself (0, then accepted values) is never a NaN
+    if (FUSE_DT && store && r >= j0 + 2 && cflv > invdt)
+      invdt = cflv;
     if (store && r >= j0 + 1)
     {
       const int jr = r - 1;
@@ -509,25 +525,25 @@ struct MarchThread
   {
     if (!FUSE_DT)
       return;
-    bool   ok = true;
+    bool   ok = a.c.lean_ok != 0;
     double q[4];
     Recip  rd;
     if (MATH == 1)
     {
       fast::prim(a.s, a.c, unD, q, rd.y);
       if (store)
-        invdt = fmax(invdt, fast::cfl_tail(a.s, rdx.y, rdy.y, q, rd.y));
+        invdt = fmax(invdt, fast::cfl_tail(a.s, a.rdx_y, a.rdy_y, q, rd.y));
       return;
     }
     prim_lean<true>(a.s, a.c, unD, q, rd, ok);
-    double v = cfl_tail_lean<true>(a.s, rdx, rdy, q, rd, ok);
+    double v = cfl_tail_lean<true>(a.s, recip_dx(a), recip_dy(a), q, rd, ok);
     if (!ok)
     {
       prim_lean<false>(a.s, a.c, unD, q, rd, ok);
-      v = cfl_tail_lean<false>(a.s, rdx, rdy, q, rd, ok);
+      v = cfl_tail_lean<false>(a.s, recip_dx(a), recip_dy(a), q, rd, ok);
     }
-    if (store)
-      invdt = fmax(invdt, v);
+    if (store && v > invdt)
+      invdt = v;
   }
 };
 

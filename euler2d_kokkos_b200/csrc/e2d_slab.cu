@@ -45,16 +45,18 @@ ld_acquire_sys(const unsigned long long * p)
   return v;
 }
 
-// Spin until *flag >= seq.  Bounded (~3 s of SM clocks): if a peer died, set the error flag and carry on with
-// garbage rather than hang the GPU; the host reports the error when it collects the state.
+// Spin until *flag >= seq.  Bounded (SlabStepArgs::timeout_clocks, 60 s of SM clocks unless E2D_PEER_TIMEOUT_S says
+// otherwise): if a peer died, raise the error flag AND `done`, so that every later step of the batch is a no-op
+// instead of marching on halo rows that never arrived; the host reports the error and marks the handle invalid.
 __device__ __forceinline__ void
-wait_flag(const unsigned long long * flag, unsigned long long seq, SlabState * st)
+wait_flag(const unsigned long long * flag, unsigned long long seq, SlabState * st, long long timeout_clocks)
 {
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < seq)
-    if (clock64() - t0 > 6000000000ll)
+    if (clock64() - t0 > timeout_clocks)
     {
       st->error = 1;
+      st->done = 1;
       break;
     }
 }
@@ -126,7 +128,7 @@ loop_scalars(const SlabStepArgs & a, bool open_next)
     s.nStep += 1;
     s.pending = 0;
   }
-  s.done = !(s.t < a.tEnd && s.nStep < a.max_steps); // main.cpp:100
+  s.done = !(s.t < a.tEnd && s.nStep < a.max_steps) || (*(volatile int *)&a.st->error != 0); // main.cpp:100
   if (open_next && !s.done)
   {
     unsigned long long bits = s.invdt_acc;
@@ -167,14 +169,14 @@ k_slab_boundaries(Geom g, BcArgs bc, double * __restrict__ A, SlabStepArgs a)
     // once the loop is over the fused steps are no-ops and publish nothing: there is nothing to wait for
     const bool over = *(volatile int *)&a.st->done != 0;
     if (a.has_lower && !over)
-      wait_flag(&a.mine->halo_flag[0], a.seq, a.st);
+      wait_flag(&a.mine->halo_flag[0], a.seq, a.st, a.timeout_clocks);
     if (a.has_upper && !over)
-      wait_flag(&a.mine->halo_flag[1], a.seq, a.st);
+      wait_flag(&a.mine->halo_flag[1], a.seq, a.st, a.timeout_clocks);
     if (blockIdx.x == 0)
     {
       if (a.nranks > 1 && !over)
         for (int k = 0; k < a.nranks; ++k)
-          wait_flag(&a.mine->invdt_flag[k], a.seq, a.st);
+          wait_flag(&a.mine->invdt_flag[k], a.seq, a.st, a.timeout_clocks);
       loop_scalars(a, true);
     }
   }

@@ -52,7 +52,9 @@ def slab_geometry(params: HydroParams, rank: int, world: int) -> SlabGeometry:
     counts, starts = partition_rows(params.ny, world)
     if min(counts) < 2:
         raise ValueError(f"ny={params.ny} is too small for {world} slabs (need >= 2 interior rows per slab)")
-    per_y = params.boundary_type_ymin == BC_PERIODIC or params.boundary_type_ymax == BC_PERIODIC
+    if world > 1 and (params.boundary_type_ymin == BC_PERIODIC) != (params.boundary_type_ymax == BC_PERIODIC):
+        # the wrap between the first and the last rank needs both y faces periodic (e2d_create refuses it as well)
+        raise ValueError("y-slabs need boundary_type_ymin and boundary_type_ymax both periodic or neither")
     faces = FACES_X
     lower = rank - 1 if rank > 0 else None
     upper = rank + 1 if rank < world - 1 else None
@@ -69,7 +71,6 @@ def slab_geometry(params: HydroParams, rank: int, world: int) -> SlabGeometry:
                 upper = 0
             else:
                 faces |= FACES_YMAX
-    del per_y
     return SlabGeometry(rank, world, counts[rank], starts[rank], counts[rank] + 4, faces, lower, upper)
 
 
@@ -140,7 +141,12 @@ class PeerSlabRun:
             dist.barrier(group=self.group)  # every rank has mapped its peers before anyone stores into them
 
     def run(self, max_steps: int):
-        """Steps until nStep == max_steps or t >= tEnd (every rank must pass the same max_steps)."""
+        """Steps until nStep == max_steps or t >= tEnd (every rank must pass the same max_steps).
+        The ranks rendezvous first: inside the loop a kernel waits for its neighbours' halo rows only for a bounded time
+        (E2D_PEER_TIMEOUT_S), so nobody may enter it while a peer is still busy elsewhere (I/O on rank 0, a gather)."""
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
         return self.hydro.run(max_steps)
 
     def current(self, nStep: int) -> torch.Tensor:

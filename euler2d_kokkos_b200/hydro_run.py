@@ -84,6 +84,7 @@ class HydroRun:
         self.jsize_loc = (slab.ny_loc if slab is not None else params.ny) + 2 * params.ghostWidth
         self.isize = params.isize
         self.shape = (4, self.jsize_loc, self.isize)
+        self._steps_taken = 0
 
     def close(self) -> None:
         if self._h:
@@ -150,11 +151,12 @@ class HydroRun:
     def run(self, max_steps: int = -1) -> RunStats:
         st = RunStats()
         check(lib().e2d_run(self._h, int(max_steps), C.byref(st)), "e2d_run")
+        self._steps_taken = max(self._steps_taken, int(st.nStep))
         return st
 
     def dt_history(self) -> np.ndarray:
-        cap = max(int(self.params.nStepmax), 1) + 1 << 1
-        buf = np.zeros(max(cap, 1 << 16))
+        """dt of every step taken by ``run`` so far (the library keeps at most 2^20 entries)."""
+        buf = np.zeros(min(max(int(self._steps_taken) + 8, 64), 1 << 20))
         n = C.c_long()
         check(lib().e2d_get_dt_history(self._h, buf.ctypes.data_as(C.POINTER(C.c_double)), buf.size, C.byref(n)),
               "e2d_get_dt_history")
@@ -162,6 +164,7 @@ class HydroRun:
 
     def set_time(self, t: float, nStep: int) -> None:
         check(lib().e2d_set_time(self._h, float(t), int(nStep)), "e2d_set_time")
+        self._steps_taken = max(self._steps_taken, int(nStep))
 
     # -- data movement --------------------------------------------------------------------------
     def download(self, which: int = E2D_U, layout: int = LAYOUT_SOA) -> np.ndarray:

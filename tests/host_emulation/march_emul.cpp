@@ -45,6 +45,8 @@ run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_lo
   a.dt = dt;
   a.d_dt = nullptr;
   a.invdt_bits = nullptr;
+  a.rdx_y = 1.0 / a.s.dx; // only the fast arithmetic reads these on the host (the strict host path divides)
+  a.rdy_y = 1.0 / a.s.dy;
   const int nx = p.nx, ny = jsize_loc - 4;
   const int nbx = (nx + (BX - 4) - 1) / (BX - 4);
   const int nseg = (ny + seg_rows - 1) / seg_rows;
@@ -58,7 +60,7 @@ run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_lo
       std::memset(sm, 0xff, sizeof(*sm)); // poison: NaNs if something is read before it is written
       bool active = true;
       for (int t = 0; t < BX; ++t)
-        active = th[t].init(a, *sm, t, bx, seg) && active;
+        active = th[t].init(a, *sm, t, bx, seg, a.d_dt ? *a.d_dt : a.dt) && active;
       if (!active)
         continue;
       for (int r = th[0].j0 - 1; r <= th[0].j1; ++r)

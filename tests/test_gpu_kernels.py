@@ -201,7 +201,13 @@ def test_lean_device_functions_match_oracle(gamma):
     assert_bitwise(out[:, :4], qo, f"prim_lean gamma={gamma}")
     inv = (co + np.abs(qo[:, 2])) / op.dx + (co + np.abs(qo[:, 3])) / op.dy
     assert_bitwise(out[:, 4], inv, f"cfl_lean gamma={gamma}")
-    assert (out[:, 5] == 1.0).mean() > 0.99
+    # the fast path is taken by every ordinary record; a density below the floor (smallr) and a momentum so small that
+    # the velocity leaves the guard window (|q| > 2^-900) are recomputed with the plain operators — exact either way
+    ordinary = np.ones(n, dtype=bool)
+    ordinary[::97] = False
+    ordinary[7::500] = False
+    assert (out[ordinary, 5] == 1.0).all()
+    assert (out[::97, 5] == 0.0).all(), "a density below smallr must leave the fast path (the floor is part of the guard)"
 
     st = np.concatenate([random_state(rng, n) for _ in range(5)], axis=1)
     st[::5, 4:8] = st[::5, 0:4]          # flat on one side -> zero slopes -> zero numerators in the trace
