@@ -15,7 +15,11 @@ state (2.1 GB per array) is far larger than the 126 MB L2, so no L2 flush is nee
           whole state host->device from pinned memory, steps, and copies it back
   roofline  fused step kernel alone: 64 B/cell (read + write 4 doubles) / its mean launch time, against the
             measured HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline  the reference's own sources (oracle/_ref) on the host cores, bounded sample
+  cpu_baseline  the reference's own sources (oracle/_ref: real Kokkos/OpenMP when built, else the test shim's loop
+                runner) on the host cores, on the same 8192 x 8192 deck the reference arm times
+  multi_gpu_parity  (every N) small decks through the same device-resident loop on the N real GPUs, gathered and
+                compared bit for bit with the CPU oracle — in the checker leg, before the timed region
+  baseline_configs  BASELINE.json configs[1], [3], [4] and the as-shipped implode deck at this N (strict build)
 """
 from __future__ import annotations
 
@@ -109,17 +113,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+REF_MAX_TIMED_STEPS = 20  # 8192^2 takes ~1 s per step on 16 cores: W + K steps of it stay within a few minutes
+REF_MAX_WARMUP = 2
+CPU_BASELINE_STEPS, CPU_BASELINE_WARMUP = 8, 1  # the `cpu_baseline` of our own line: the same deck, fewer steps
+
+
 def run_reference_sample(nx: int, ny: int, steps: int, warmup: int, threads: int | None = None):
-    """Time the reference's own sources (oracle/_ref/ref_dump) on the host cores."""
+    """Time the reference's own sources on the host cores: oracle/_ref/ref_dump_kokkos (the reference on its real
+    Kokkos 5.1.0 / OpenMP runtime, baseline/build_ref_omp.sh) when present, else oracle/_ref/ref_dump (the same
+    sources on the test shim's OpenMP loop runner; bit-identical results, tests/test_oracle_pins.py)."""
     import oracle
     from euler2d_kokkos_b200.decks import write_deck
 
     if not oracle.ref_available():
         oracle.build()
     exe = oracle.ref_binary()
-    kind = "reference"
     if not os.path.exists(exe):
         return None
+    runtime = "Kokkos 5.1.0 OpenMP backend" if exe.endswith("_kokkos") else "oracle/kokkos_shim OpenMP loop runner"
     threads = threads or os.cpu_count() or 1
     with tempfile.TemporaryDirectory() as td:
         ini = write_deck(os.path.join(td, "ref.ini"), "four_quadrant", **workload_overrides(1, nx, ny))
@@ -130,8 +141,10 @@ def run_reference_sample(nx: int, ny: int, steps: int, warmup: int, threads: int
         wall = time.perf_counter() - t0
     meta = json.loads(out.strip().splitlines()[-1])
     return {"value": meta["mcell_updates_per_s"], "unit": UNIT, "cores": int(meta.get("threads", threads)),
-            "kind": kind, "sample": f"four_quadrant {nx}x{ny}, {meta['timed_steps']} timed steps after {warmup} "
-                                    f"warm-up, impl 0, OMP_NUM_THREADS={threads} ({os.path.basename(exe)})",
+            "kind": "reference", "runtime": runtime, "host_cpus": os.cpu_count(),
+            "sample": f"four_quadrant {nx}x{ny} (the bench workload of one GPU), {meta['timed_steps']} timed steps after "
+                      f"{warmup} warm-up, implementationVersion 0, OMP_NUM_THREADS={threads} ({os.path.basename(exe)}: "
+                      f"{runtime})",
             "loop_seconds": meta["loop_seconds"], "wall_seconds": round(wall, 2), "timed_steps": meta["timed_steps"]}
 
 
@@ -139,24 +152,206 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # bounded sample: 2048^2 cells per step keeps W+K steps within minutes on any host
-    nx = ny = 2048
-    res = run_reference_sample(nx, ny, args.steps, args.warmup)
+    # the real deck of one GPU (8192 x 8192); the number of timed steps is bounded so that the run ends within minutes
+    steps = max(1, min(args.steps, REF_MAX_TIMED_STEPS))
+    warmup = max(0, min(args.warmup, REF_MAX_WARMUP))
+    res = run_reference_sample(NX_PER_GPU, NY_PER_GPU, steps, warmup)
     if res is None:
         emit({"impl": "reference", "unavailable": "oracle/_ref/ref_dump missing and /root/reference absent"})
         return 0
     ms = res["loop_seconds"] / max(res["timed_steps"], 1) * 1e3
-    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+    cfg = config_dict(args.gpus)
+    cfg["reference_sample"] = (f"CPU arm: one GPU's share of the workload ({NX_PER_GPU}x{NY_PER_GPU} cells, the whole deck "
+                               f"at N=1), {steps} timed steps after {warmup} warm-up (asked: {args.steps} / {args.warmup})")
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "impl": "reference",
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "runtime", "host_cpus", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "each step is a bounded sample (2048x2048 cells) of the workload; Mcell-updates/s is size "
-                    "independent beyond cache"}
+            "steps_asked": args.steps, "warmup_asked": args.warmup}
+    kk = kokkos_openmp_program(NX_PER_GPU, NY_PER_GPU, min(steps, 10))
+    if kk:
+        line["reference_program"] = kk
     emit(line)
     return 0
+
+
+def kokkos_openmp_program(nx: int, ny: int, steps: int):
+    """The reference's own PROGRAM (src/main.cpp, real Kokkos/OpenMP: baseline/_ref/euler2d_kokkos_omp) on the same
+    deck, its own `Perf` line (initialisation and ghost cells included): reported beside the loop timer above."""
+    import re
+
+    from euler2d_kokkos_b200.decks import write_deck
+
+    exe = os.path.join(ROOT, "baseline", "_ref", "euler2d_kokkos_omp")
+    if not os.path.exists(exe):
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            ini = write_deck(os.path.join(td, "ref.ini"), "four_quadrant",
+                             **dict(workload_overrides(1, nx, ny), run__nStepmax=steps))
+            env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1), OMP_PROC_BIND="spread", OMP_PLACES="threads")
+            out = subprocess.run([exe, ini], capture_output=True, text=True, env=env, cwd=td, timeout=900).stdout
+        m = re.search(r"Perf\s*:\s*([0-9.]+)", out)
+        if not m:
+            return None
+        perf = float(m.group(1))
+        return {"value": perf * (nx * ny) / ((nx + 4) * (ny + 4)), "unit": UNIT, "steps": steps, "cores": os.cpu_count(),
+                "kind": "unmodified reference program, Kokkos 5.1.0 OpenMP backend, its own total-time clock"}
+    except Exception as ex:  # evidence only
+        return {"value": None, "error": str(ex)[:200]}
+
+
+# ------------------------------------------------------------------------------------------ checker leg
+PERIODIC = dict(mesh__boundary_type_xmin=3, mesh__boundary_type_xmax=3, mesh__boundary_type_ymin=3,
+                mesh__boundary_type_ymax=3)
+PARITY_DECKS = [  # (label, deck, overrides, steps): the reference's decks at oracle-sized grids, every boundary kind
+    ("implode 256x128 (as shipped), 100 steps", "implode", dict(), 100),
+    ("shocked_bubble 178x37, 60 steps", "shocked_bubble", dict(mesh__nx=178, mesh__ny=37), 60),
+    ("implode 96x50 periodic (y wraps rank N-1 -> rank 0), 60 steps", "implode", dict(mesh__nx=96, mesh__ny=50, **PERIODIC), 60),
+    ("four_quadrant 200x120 absorbing, 60 steps", "four_quadrant", dict(mesh__nx=200, mesh__ny=120), 60),
+]
+
+
+def device_loop_parity(dev, rank, world):
+    """The device-resident loop on the N real GPUs of this run (PeerSlabRun: NVLink peer stores + flags between the
+    ranks; one rank: the single-GPU loop) against the CPU oracle, bit for bit: final interior, dt of every step, step
+    count, final time.  Checker leg: nothing here is timed.  Raises on a mismatch — a bench line is only printed for a
+    library that reproduces the reference."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import euler2d_kokkos_b200 as e2d
+    from euler2d_kokkos_b200.decks import deck_text
+    from euler2d_kokkos_b200.distributed import PeerSlabRun
+
+    decks, ok_all = [], True
+    for label, deck, ov, steps in PARITY_DECKS:
+        text = deck_text(deck, run__nOutput=-1, **ov)
+        hp = e2d.HydroParams.from_string(text)
+        run = PeerSlabRun(hp, rank=rank, world=world, device=dev)
+        st = run.run(steps)
+        U = run.gather_interior(st.nStep)
+        dts = run.hydro.dt_history()
+        run.close()
+        verdict = None
+        if rank == 0:
+            import oracle
+
+            with tempfile.TemporaryDirectory() as td:
+                ini = os.path.join(td, "deck.ini")
+                with open(ini, "w") as f:
+                    f.write(text)
+                op = oracle.params_from_ini(ini)
+            U_ref, dts_ref, n_ref, t_ref = oracle.run(op, steps)
+            Uh = U.cpu().numpy()
+            same_state = bool(np.array_equal(Uh.view(np.uint64), np.ascontiguousarray(U_ref[:, 2:-2, 2:-2]).view(np.uint64)))
+            same_dt = bool(len(dts) == n_ref and np.array_equal(dts, dts_ref[1:]))
+            verdict = {"deck": label, "steps": int(st.nStep), "state_bitwise": same_state, "dt_history_bitwise": same_dt,
+                       "same_step_count": bool(st.nStep == n_ref), "same_final_time": bool(st.t == t_ref)}
+            ok_all = ok_all and same_state and same_dt and st.nStep == n_ref and st.t == t_ref
+            decks.append(verdict)
+    if world > 1:
+        flag = torch.tensor([1 if ok_all else 0], device=dev)
+        dist.broadcast(flag, 0)
+        ok_all = bool(flag.item())
+    res = {"bitwise": ok_all, "n_gpus": world, "against": "CPU oracle (oracle/euler2d_oracle.c, pinned to the reference)",
+           "path": "PeerSlabRun -> e2d_run: " + ("halo rows + invDt partials as NVLink peer stores between the ranks"
+                                                  if world > 1 else "single-GPU loop, one launch per step"),
+           "decks": decks}
+    if not ok_all:
+        if rank == 0:
+            print(json.dumps({"multi_gpu_parity": res}), file=sys.stderr)
+        raise SystemExit("bench.py: the device-resident loop on the real GPUs does NOT reproduce the oracle bit for bit")
+    return res
+
+
+def timed_config(dev, rank, world, deck, nx, ny, steps, warmup=3, **ov):
+    """One BASELINE config through the device-resident loop on this run's GPUs (strict build): CUDA events inside
+    e2d_run, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    import euler2d_kokkos_b200 as e2d
+    from euler2d_kokkos_b200.decks import deck_text
+    from euler2d_kokkos_b200.distributed import PeerSlabRun
+
+    hp = e2d.HydroParams.from_string(deck_text(deck, mesh__nx=nx, mesh__ny=ny, run__nOutput=-1, run__nStepmax=10 ** 8,
+                                               run__tEnd=1e9, **ov))
+    run = PeerSlabRun(hp, rank=rank, world=world, device=dev)
+    run.run(warmup)
+    torch.cuda.synchronize()
+    st = run.run(warmup + steps)
+    sec = st.seconds
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    run.close()
+    return {"deck": deck, "nx": nx, "ny": ny, "n_gpus": world, "steps": steps, "ms_per_step": sec / steps * 1e3,
+            "value": nx * ny * steps / sec * 1e-6, "unit": UNIT,
+            "state_GB_per_gpu": round(2 * 4 * 8 * (nx + 4) * (ny // world + 4) * 1e-9, 2)}
+
+
+N1_RATES_FILE = os.path.join(tempfile.gettempdir(), "e2d_bench_n1_rates.json")
+
+
+def baseline_configs(dev, rank, world):
+    """BASELINE.json configs beside the headline (configs[2]): [1] blast 1024x1536 and the as-shipped implode deck at
+    N=1; [3] implode_big / blast 16384^2 split N ways (strong scaling); [4] shocked_bubble 32768^2 strong-split and
+    32768 x 4096 per GPU (weak).  `efficiency` = rate / (N x the N=1 rate of the same deck and per-GPU size), with the
+    N=1 rates taken from this box's own N=1 run when it left them in the temp directory (the driver runs N=1 first)."""
+    out = {}
+    n1 = {}
+    if world > 1:
+        try:
+            n1 = json.load(open(N1_RATES_FILE))
+        except Exception:
+            n1 = {}
+
+    def add(key, row, n1_key=None):
+        base = n1.get(n1_key or key)
+        row["efficiency_vs_n1"] = (row["value"] / (world * base)) if (base and world > 1) else None
+        out[key] = row
+
+    if world == 1:
+        add("blast_1024x1536", timed_config(dev, rank, world, "blast", 1024, 1536, 200))
+        r = timed_config(dev, rank, world, "implode", 256, 128, 400)
+        r["us_per_step"] = r["ms_per_step"] * 1e3
+        add("implode_as_shipped_256x128", r)
+    # configs[3]: 16384^2, strong scaling (the whole grid also fits one B200: 2 x 8.6 GB)
+    add("implode_big_16384_strong", timed_config(dev, rank, world, "implode_big", 16384, 16384, 10))
+    add("blast_16384_strong", timed_config(dev, rank, world, "blast", 16384, 16384, 10))
+    # configs[4]: shocked_bubble, 32768 columns.  weak: 4096 rows per GPU.  strong: 32768^2 (2 x 34 GB on one GPU)
+    add("shocked_bubble_32768x4096_per_gpu_weak", timed_config(dev, rank, world, "shocked_bubble", 32768, 4096 * world, 10,
+                                                               mesh__xmax=3.2768, mesh__ymax=0.4096 * world))
+    if world in (1, 8):
+        add("shocked_bubble_32768_strong", timed_config(dev, rank, world, "shocked_bubble", 32768, 32768, 5,
+                                                        mesh__xmax=3.2768, mesh__ymax=3.2768))
+    if world == 1 and rank == 0:
+        try:
+            json.dump({k: v["value"] for k, v in out.items()}, open(N1_RATES_FILE, "w"))
+        except Exception:
+            pass
+    if world > 1:
+        out["_n1_rates_source"] = N1_RATES_FILE if n1 else "absent: run `bench.py --gpus 1` on this box first"
+    return out
+
+
+def csrc_sha():
+    """sha256 over the CUDA sources the kernels are built from: profiles/roofline_traffic.json carries the value it was
+    captured at, so a stale ncu capture is visible in the bench line (`traffic_stale`)."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "euler2d_kokkos_b200", "csrc", "*.cu*"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -194,6 +389,8 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     K, W = args.steps, max(args.warmup, 3)
+    # checker leg first: the loop that is about to be timed, on these very GPUs, against the CPU oracle (bit for bit)
+    parity = None if args.no_parity else device_loop_parity(dev, rank, world)
     hp = e2d.HydroParams.from_string(deck_text("four_quadrant", **workload_overrides(world)))
     cells_total = hp.nx * hp.ny
     launches0 = e2d.lib().e2d_kernel_launch_count()
@@ -275,11 +472,14 @@ def ours(args):
         cells_per_launch = NX_PER_GPU * NY_PER_GPU  # one launch = one GPU's slab
         achieved = ALGO_BYTES_PER_CELL * cells_per_launch / per_launch * 1e-9
         traffic = prof.get("k_fused_step_8192x8192")
+        sha_now = csrc_sha()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                    "traffic": traffic, "kernel": "k_fused_step<HLLC, fused dt>", "kernel_ms_per_launch": per_launch * 1e3,
+                    "traffic": traffic, "traffic_csrc_sha": prof.get("csrc_sha"), "csrc_sha": sha_now,
+                    "traffic_stale": prof.get("csrc_sha") != sha_now,
+                    "kernel": "k_fused_step<HLLC, fused dt>", "kernel_ms_per_launch": per_launch * 1e3,
                     "kernel_share_of_step": kernel_seconds / seconds, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL * cells_per_launch,
-                    "note": "the strict fp64 step is FP64-pipe / issue bound, not HBM bound (DESIGN.md section 4): ~500 "
+                    "note": "the strict fp64 step is FP64-pipe / issue bound, not HBM bound (DESIGN.md section 4): ~470 "
                             "FP64-pipe warp instructions per 32 cells against 64 B per cell"}
         # the resource that actually binds: FP64 pipe occupancy = (FP64 warp instructions per launch, counted by ncu)
         # / (launch time x 592 SM sub-partitions x SM clock) against the pipe rate measured by tools/microbench
@@ -485,13 +685,22 @@ def ours(args):
             except Exception as ex:  # evidence only
                 extra["reference_gpu"] = {"value": None, "error": str(ex)[:200]}
             try:
-                cpu_baseline = run_reference_sample(4096, 4096, 6, 1)
+                # the same deck the reference arm times (8192 x 8192), fewer steps: one record, one CPU number
+                cpu_baseline = run_reference_sample(NX_PER_GPU, NY_PER_GPU, CPU_BASELINE_STEPS, CPU_BASELINE_WARMUP)
                 if cpu_baseline:
-                    cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "runtime", "host_cpus",
+                                                                 "sample")}
             except Exception as ex:  # never lose the GPU number to a CPU-side problem
                 cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
 
+    configs = None
+    if not args.no_configs:
+        if distributed:
+            run.close()
+        configs = baseline_configs(dev, rank, world)
     if rank == 0:
+        extra["multi_gpu_parity"] = parity
+        extra["baseline_configs"] = configs
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": seconds / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config_dict(world), "roofline": roofline,
@@ -514,6 +723,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the `arithmetic=fast` measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bitwise check against the oracle (development)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (development)")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON): everything else a library may print on file descriptor 1 (NCCL's
     # version banner, for instance) goes to stderr

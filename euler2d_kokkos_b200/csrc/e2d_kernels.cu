@@ -699,7 +699,7 @@ solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
 
 // LOOP: 0 = one step, dt from the arguments;  1 = multi-GPU slab loop (publishes halo rows + invDt partial to the
 // peers, e2d_slab.cu);  2 = single-GPU loop with one launch per step (SoloLoop: dt, boundary push, bookkeeping).
-template <int SOLVER, bool FUSE_DT, int LOOP, int MATH = 0, bool TYP = false>
+template <int SOLVER, bool FUSE_DT, int LOOP, int MATH = 0, int TYP = 0>
 __global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
 k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_done,
              const __grid_constant__ FusedLink link, const __grid_constant__ SoloLoop solo)
@@ -1348,7 +1348,7 @@ configure_once(K kernel, size_t smem, std::atomic<unsigned long long> & done_mas
   return e;
 }
 
-template <int SOL, bool FUSE, int LOOP, int MATH, bool TYP>
+template <int SOL, bool FUSE, int LOOP, int MATH, int TYP>
 cudaError_t
 launch_instance(const dim3 & grid, size_t smem, cudaStream_t st, bool pdl, const MarchArgs & a, const int * d_done,
                 const FusedLink & lk, const SoloLoop & so)
@@ -1371,7 +1371,7 @@ launch_instance(const dim3 & grid, size_t smem, cudaStream_t st, bool pdl, const
 }
 
 // mode: 0 plain without the fused CFL reduction, 1 plain with it, 2 peers (multi-GPU loop), 3 solo (single-GPU loop)
-template <int SOL, int MATH, bool TYP>
+template <int SOL, int MATH, int TYP>
 cudaError_t
 launch_mode(int mode, const dim3 & grid, size_t smem, cudaStream_t st, bool pdl, const MarchArgs & a,
             const int * d_done, const FusedLink & lk, const SoloLoop & so)
@@ -1450,20 +1450,22 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     so = *solo;
     mode = 3;
   }
-  // the common case as its own instantiation (HLLC, strict): limited slopes on square cells (MarchThread<.., TYP>)
-  const bool   typ = a.c.limited && p.dx == p.dy;
+  // what is known about the deck becomes a template argument of the HLLC strict kernel (MarchThread<.., TYP>)
+  const int    typ = !a.c.limited ? 0 : (p.dx == p.dy ? 1 : 2);
   const size_t smem = sizeof(MarchSmem<kBX>);
   cudaError_t  launch_err;
   if (sol == E2D_RIEMANN_APPROX)
-    launch_err = launch_mode<0, 0, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+    launch_err = launch_mode<0, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (sol == E2D_RIEMANN_HLL)
-    launch_err = launch_mode<1, 0, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+    launch_err = launch_mode<1, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (fastm)
-    launch_err = launch_mode<2, 1, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
-  else if (typ)
-    launch_err = launch_mode<2, 0, true>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+    launch_err = launch_mode<2, 1, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (typ == 1)
+    launch_err = launch_mode<2, 0, 1>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (typ == 2)
+    launch_err = launch_mode<2, 0, 2>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else
-    launch_err = launch_mode<2, 0, false>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+    launch_err = launch_mode<2, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   count_launch();
   return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
 }
@@ -1482,11 +1484,12 @@ preload_step_kernels()
     e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, true, 0, MATH, TYP>);      \
   if (e == cudaSuccess)                                                         \
     e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, false, 0, MATH, TYP>);
-  E2D_PRE(0, 0, false)
-  E2D_PRE(1, 0, false)
-  E2D_PRE(2, 0, false)
-  E2D_PRE(2, 0, true)
-  E2D_PRE(2, 1, false)
+  E2D_PRE(0, 0, 0)
+  E2D_PRE(1, 0, 0)
+  E2D_PRE(2, 0, 0)
+  E2D_PRE(2, 0, 1)
+  E2D_PRE(2, 0, 2)
+  E2D_PRE(2, 1, 0)
 #undef E2D_PRE
   return e;
 }

@@ -160,13 +160,17 @@ st4(Pair (&row)[2][BX], int t, const double v[4])
 // reciprocal-multiply division, within north_star's 1e-12 of the reference; `[other] arithmetic=fast`).  With
 // MATH == 1 the RY ring holds the fast reciprocal of the density, FX / fyP carry UNSCALED fluxes (the update applies
 // dt/dx, dt/dy inside its fma chain) and the solver is the fast HLLC when SOLVER == 2.
-// TYP: the common case known at compile time — limited slopes (slope_type 1 or 2) on square cells (dx == dy, hence
-// dt/dx == dt/dy): every deck of the reference.  The generic instantiation tests both at run time, which costs the
-// strict kernel ~40 issue slots per row (predicated multiplies, selects against zero slopes, two DSETPs).
-template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0, bool TYP = false>
+// TYP: what is known about the deck at compile time.  1: limited slopes (slope_type 1 or 2) on square cells (dx == dy
+// bit for bit, hence dt/dx == dt/dy) — four of the reference's five decks;  2: limited slopes, dx != dy (its
+// shocked_bubble deck: 0.445f/445 and 0.089f/89 differ in the last bits);  0: nothing — slope_type and dx == dy are
+// tested at run time, which costs the strict kernel ~40 issue slots per row (predicated multiplies, selects against
+// zero slopes, two DSETPs).
+template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0, int TYP = 0>
 struct MarchThread
 {
   static constexpr bool PACK = (MATH == 1); // shared-memory rows as 16-byte pairs
+  static constexpr bool LIMITED = (TYP != 0);
+  static constexpr bool SQUARE = (TYP == 1);
   static constexpr bool UNFL = E2D_WINDOW_GUARDS != 0; // face densities left unfloored (e2d_lean.cuh)
   // geometry
   int    t, tm, tp; // lane in the block, clamped west / east lanes
@@ -198,8 +202,8 @@ struct MarchThread
   recip_dy(const MarchArgs & a)
   {
     Recip r;
-    r.d = TYP ? a.s.dx : a.s.dy;
-    r.y = TYP ? a.rdx_y : a.rdy_y;
+    r.d = SQUARE ? a.s.dx : a.s.dy;
+    r.y = SQUARE ? a.rdx_y : a.rdy_y;
     return r;
   }
 
@@ -332,7 +336,7 @@ struct MarchThread
     rd.y = sm.RY[sC][t];
 
     // slope_unsplit_hydro_2d (src/HydroBaseFunctor.h:473-516): slope_type outside {1,2} -> zero slopes
-    const bool limited = TYP || a.c.limited != 0;
+    const bool limited = LIMITED || a.c.limited != 0;
     if (MATH == 1)
     {
       const double st0 = limited ? s.slope_type : 0.0;
@@ -342,14 +346,14 @@ struct MarchThread
     }
     else
     {
-      slopes_lean<TYP>(s.slope_type, limited, qC, qE, qW, dqX);
-      slopes_lean<TYP>(s.slope_type, limited, qC, qN, qS, dqY);
+      slopes_lean<LIMITED>(s.slope_type, limited, qC, qE, qW, dqX);
+      slopes_lean<LIMITED>(s.slope_type, limited, qC, qN, qS, dqY);
 
       bool ok = a.c.lean_ok != 0;
       trace_sources_lean<true>(s, qC, rd, dqX, dqY, s0, ok);
       if (!ok)
         trace_sources_lean<false>(s, qC, rd, dqX, dqY, s0, ok);
-      trace_faces_lean<TYP, UNFL>(s, qC, dqX, dqY, s0, dtdx, TYP ? dtdx : dtdy, xmin, xmax, ymin, ymax);
+      trace_faces_lean<TYP, UNFL>(s, qC, dqX, dqY, s0, dtdx, SQUARE ? dtdx : dtdy, xmin, xmax, ymin, ymax);
     }
 
     st4<PACK>(sm.XMAX[r & 1], t, xmax);
@@ -386,7 +390,7 @@ struct MarchThread
     for (int v = 0; v < 4; ++v)
     {
       fx[v] = fx[v] * dtdx;
-      fy[v] = fy[v] * (TYP ? dtdx : dtdy);
+      fy[v] = fy[v] * (SQUARE ? dtdx : dtdy);
     }
     // complete row r-1: UpdateFunctor order (HydroRunFunctors.h:695-713)
     E2D_UNROLL
