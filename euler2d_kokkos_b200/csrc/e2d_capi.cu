@@ -494,7 +494,8 @@ extern "C"
                   { "approx", 4, 8, 8 }, { "cmpflx", 5, 4, 4 }, { "hll", 6, 8, 4 },     { "hllc_lean", 7, 8, 5 },
                   { "cell_lean", 8, 4, 6 }, { "trace_lean", 9, 22, 25 }, { "div", 10, 2, 5 }, { "sqrt", 11, 1, 3 },
                   { "fast_div", 12, 2, 2 }, { "fast_sqrt", 13, 1, 2 }, { "fast_hllc", 14, 8, 4 },
-                  { "fast_cell", 15, 4, 5 }, { "fast_slope", 16, 20, 8 }, { "fast_trace", 17, 14, 16 } };
+                  { "fast_cell", 15, 4, 5 }, { "fast_slope", 16, 20, 8 }, { "fast_trace", 17, 14, 16 },
+                  { "rusanov", 18, 8, 4 } };
     int id = -1, nin = 0, nout = 0;
     for (const auto & e : table)
       if (!std::strcmp(e.name, func))

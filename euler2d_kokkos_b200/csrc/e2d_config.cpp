@@ -204,6 +204,8 @@ setup(const Config & cfg, e2d_params * p)
     p->riemannSolverType = E2D_RIEMANN_HLL;
   else if (riemann == "hllc")
     p->riemannSolverType = E2D_RIEMANN_HLLC;
+  else if (riemann == "rusanov" || riemann == "llf") // extension (the reference would print the message below)
+    p->riemannSolverType = E2D_RIEMANN_RUSANOV;
   else
   {
     std::printf("Riemann Solver specified in parameter file is invalid\n");

@@ -174,6 +174,8 @@ slopes(double st_or_zero, const double q[4], const double qPlus[4], const double
 
 // trace_unsplit_2d_along_dir (src/HydroBaseFunctor.h:245-289), all four faces of one cell.  n0 = -s0 (the source
 // terms with the sign pulled out); face = q -+ dq/2 + s0*dtdir/2, evaluated as fma(+-0.5, dq, fma(-n0, dtdir/2, q)).
+// SQUARE: dx == dy is known at compile time (MarchThread<.., TYP = 1>); else tested at run time
+template <bool SQUARE = false>
 E2D_HD void
 trace(const Settings & s, const double q[4], double ry, const double dqX[4], const double dqY[4], double hdtdx,
       double hdtdy, double xmin[4], double xmax[4], double ymin[4], double ymax[4])
@@ -189,7 +191,7 @@ trace(const Settings & s, const double q[4], double ry, const double dqX[4], con
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     cx[k] = cy[k] = fmadd(-n0[k], hdtdx, q[k]);
-  if (hdtdx != hdtdy) // square cells (every deck of the reference): the half-step predictor is shared by x and y
+  if (!SQUARE && hdtdx != hdtdy) // square cells: the half-step predictor is shared by x and y
   {
 #pragma unroll
     for (int k = 0; k < 4; ++k)

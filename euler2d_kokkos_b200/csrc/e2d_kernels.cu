@@ -39,6 +39,10 @@ constexpr int kMarchMinBlocksFast = E2D_FAST_MIN_BLOCKS; // same for the `arithm
 // rows per trip of the marching loop of the fast instantiations (ring slot r & 1 becomes a constant, fewer carried
 // register moves: +2 %; the strict kernel, at 158 registers, loses 4 % to the same unrolling)
 constexpr int kMarchUnrollFast = E2D_MARCH_UNROLL;
+#ifndef E2D_STRICT_UNROLL
+#  define E2D_STRICT_UNROLL 1
+#endif
+constexpr int kMarchUnrollStrict = E2D_STRICT_UNROLL;
 constexpr int
 march_min_blocks(int math)
 {
@@ -733,7 +737,7 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
   if (active)
   {
     __syncthreads();
-#pragma unroll(MATH == 1 ? kMarchUnrollFast : 1)
+#pragma unroll(MATH == 1 ? kMarchUnrollFast : kMarchUnrollStrict)
     for (int r = th.j0 - 1; r <= th.j1; ++r)
     {
       th.phaseA(a, sm, r);
@@ -992,6 +996,14 @@ k_eval(Settings s, int func, const double * __restrict__ in, double * __restrict
       fast::trace(s, a, fast::rcp(a[ID]), a + 4, a + 8, 0.5 * a[12], 0.5 * a[13], o, o + 4, o + 8, o + 12);
       break;
     }
+    case 18:
+    { // rusanov: same record as hllc
+      const double * a = in + 8 * r;
+      double *       o = out + 4 * r;
+      riemann_rusanov(s, a[ID], a[IP], a[IU], a[IV], a[4 + ID], a[4 + IP], a[4 + IU], a[4 + IV], o[ID], o[IP], o[IU],
+                      o[IV]);
+      break;
+    }
     case 5:
     { // cmpflx
       const double * a = in + 4 * r;
@@ -1179,6 +1191,9 @@ launch_compute_and_store_fluxes(const e2d_params & p, const Geom & g, const doub
     case E2D_RIEMANN_HLL:
       k_compute_and_store_fluxes<1><<<grid, 128, 0, st>>>(g, s, Q, Fx, Fy, dtdx, dtdy);
       break;
+    case E2D_RIEMANN_RUSANOV:
+      k_compute_and_store_fluxes<3><<<grid, 128, 0, st>>>(g, s, Q, Fx, Fy, dtdx, dtdy);
+      break;
     default:
       k_compute_and_store_fluxes<2><<<grid, 128, 0, st>>>(g, s, Q, Fx, Fy, dtdx, dtdy);
   }
@@ -1217,6 +1232,8 @@ launch_trace_and_fluxes(const e2d_params & p, const Geom & g, const double * Q, 
       E2D_TF(0, 1);
     else if (sol == 1)
       E2D_TF(1, 1);
+    else if (sol == 3)
+      E2D_TF(3, 1);
     else
       E2D_TF(2, 1);
   }
@@ -1226,6 +1243,8 @@ launch_trace_and_fluxes(const e2d_params & p, const Geom & g, const double * Q, 
       E2D_TF(0, 2);
     else if (sol == 1)
       E2D_TF(1, 2);
+    else if (sol == 3)
+      E2D_TF(3, 2);
     else
       E2D_TF(2, 2);
   }
@@ -1458,6 +1477,10 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     launch_err = launch_mode<0, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (sol == E2D_RIEMANN_HLL)
     launch_err = launch_mode<1, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (sol == E2D_RIEMANN_RUSANOV)
+    launch_err = launch_mode<3, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (fastm && typ == 1)
+    launch_err = launch_mode<2, 1, 1>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (fastm)
     launch_err = launch_mode<2, 1, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (typ == 1)
@@ -1486,10 +1509,12 @@ preload_step_kernels()
     e = cudaFuncGetAttributes(&fa, k_fused_step<SOL, false, 0, MATH, TYP>);
   E2D_PRE(0, 0, 0)
   E2D_PRE(1, 0, 0)
+  E2D_PRE(3, 0, 0)
   E2D_PRE(2, 0, 0)
   E2D_PRE(2, 0, 1)
   E2D_PRE(2, 0, 2)
   E2D_PRE(2, 1, 0)
+  E2D_PRE(2, 1, 1)
 #undef E2D_PRE
   return e;
 }

@@ -168,7 +168,10 @@ st4(Pair (&row)[2][BX], int t, const double v[4])
 template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0, int TYP = 0>
 struct MarchThread
 {
-  static constexpr bool PACK = (MATH == 1); // shared-memory rows as 16-byte pairs
+#ifndef E2D_STRICT_PACK
+#  define E2D_STRICT_PACK 1
+#endif
+  static constexpr bool PACK = (MATH == 1) || E2D_STRICT_PACK; // shared-memory rows as 16-byte pairs
   static constexpr bool LIMITED = (TYP != 0);
   static constexpr bool SQUARE = (TYP == 1);
   static constexpr bool UNFL = E2D_WINDOW_GUARDS != 0; // face densities left unfloored (e2d_lean.cuh)
@@ -342,7 +345,7 @@ struct MarchThread
       const double st0 = limited ? s.slope_type : 0.0;
       fast::slopes(st0, qC, qE, qW, dqX);
       fast::slopes(st0, qC, qN, qS, dqY);
-      fast::trace(s, qC, rd.y, dqX, dqY, hdtdx, hdtdy, xmin, xmax, ymin, ymax);
+      fast::trace<SQUARE>(s, qC, rd.y, dqX, dqY, hdtdx, SQUARE ? hdtdx : hdtdy, xmin, xmax, ymin, ymax);
     }
     else
     {
@@ -460,7 +463,10 @@ struct MarchThread
     // complete row r-1: U + Fx(i) - Fx(i+1) + Fy(j) - Fy(j+1) (HydroRunFunctors.h:695-713), pend = U + Fx(i)
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
-      un[v] = fast::fmadd(-fy[v], dtdy, fast::fmadd(fyP[v], dtdy, fast::fmadd(-fxE[v], dtdx, pend[v])));
+    {
+      const double dty = SQUARE ? dtdx : dtdy;
+      un[v] = fast::fmadd(-fy[v], dty, fast::fmadd(fyP[v], dty, fast::fmadd(-fxE[v], dtdx, pend[v])));
+    }
     cflv = 0.0;
     if (FUSE_DT)
     {

@@ -390,7 +390,33 @@ riemann_hll(const Settings & s, double rl_in, double pl_in, double ul, double vl
   }
 }
 
-// Riemann solve at a face, selected at compile time.  solver: 0 approx, 1 hll, 2 hllc.
+// Rusanov (local Lax-Friedrichs) flux.  NOT in the reference either (north_star names "approximate (Rusanov/HLL)"
+// solvers) — an extension behind `honourRiemannSolver` + `riemann=rusanov`.  Parity unpinned by construction; the
+// oracle carries a CPU restatement of the same formula (e2do_riemann_rusanov) that this is bit-identical to.
+//   F = (FL + FR)/2 - smax (UR - UL)/2,  smax = max(|ul| + cl, |ur| + cr), floors and sound speeds as in riemann_hllc
+E2D_HD void
+riemann_rusanov(const Settings & s, double rl_in, double pl_in, double ul, double vl, double rr_in, double pr_in,
+                double ur, double vr, double & f_d, double & f_e, double & f_n, double & f_t)
+{
+  const double entho = 1.0 / (s.gamma0 - 1.0);
+  double       rl = fmax(rl_in, s.smallr);
+  double       pl = fmax(pl_in, rl * s.smallp);
+  double       rr = fmax(rr_in, s.smallr);
+  double       pr = fmax(pr_in, rr * s.smallp);
+  double       etotl = pl * entho + 0.5 * rl * (ul * ul + vl * vl);
+  double       etotr = pr * entho + 0.5 * rr * (ur * ur + vr * vr);
+  double       cl = sqrt(fmax(s.gamma0 * pl / rl, s.smallc * s.smallc));
+  double       cr = sqrt(fmax(s.gamma0 * pr / rr, s.smallc * s.smallc));
+  double       smax = fmax(fabs(ul) + cl, fabs(ur) + cr);
+  double       fl_d = rl * ul, fl_n = rl * ul * ul + pl, fl_t = rl * ul * vl, fl_e = (etotl + pl) * ul;
+  double       fr_d = rr * ur, fr_n = rr * ur * ur + pr, fr_t = rr * ur * vr, fr_e = (etotr + pr) * ur;
+  f_d = 0.5 * (fl_d + fr_d) - 0.5 * smax * (rr - rl);
+  f_n = 0.5 * (fl_n + fr_n) - 0.5 * smax * (rr * ur - rl * ul);
+  f_t = 0.5 * (fl_t + fr_t) - 0.5 * smax * (rr * vr - rl * vl);
+  f_e = 0.5 * (fl_e + fr_e) - 0.5 * smax * (etotr - etotl);
+}
+
+// Riemann solve at a face, selected at compile time.  solver: 0 approx, 1 hll, 2 hllc, 3 rusanov.
 template <int solver>
 E2D_HD void
 riemann(const Settings & s, double rl, double pl, double ul, double vl, double rr, double pr, double ur,
@@ -400,6 +426,8 @@ riemann(const Settings & s, double rl, double pl, double ul, double vl, double r
     riemann_hllc(s, rl, pl, ul, vl, rr, pr, ur, vr, f_d, f_e, f_n, f_t);
   else if (solver == 1)
     riemann_hll(s, rl, pl, ul, vl, rr, pr, ur, vr, f_d, f_e, f_n, f_t);
+  else if (solver == 3)
+    riemann_rusanov(s, rl, pl, ul, vl, rr, pr, ur, vr, f_d, f_e, f_n, f_t);
   else
   {
     double g_d, g_p, g_n, g_t;

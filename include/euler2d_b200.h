@@ -41,7 +41,8 @@ enum { E2D_FACE_XMIN = 0, E2D_FACE_XMAX = 1, E2D_FACE_YMIN = 2, E2D_FACE_YMAX = 
 enum { E2D_BC_UNDEFINED = 0, E2D_BC_DIRICHLET = 1, E2D_BC_NEUMANN = 2, E2D_BC_PERIODIC = 3, E2D_BC_COPY = 4 };
 enum { E2D_PROBLEM_IMPLODE = 0, E2D_PROBLEM_BLAST = 1, E2D_PROBLEM_FOUR_QUADRANT = 2,
        E2D_PROBLEM_DISCONTINUITY = 3, E2D_PROBLEM_SHOCKED_BUBBLE = 4 };
-enum { E2D_RIEMANN_APPROX = 0, E2D_RIEMANN_HLL = 1, E2D_RIEMANN_HLLC = 2 };
+enum { E2D_RIEMANN_APPROX = 0, E2D_RIEMANN_HLL = 1, E2D_RIEMANN_HLLC = 2,
+       E2D_RIEMANN_RUSANOV = 3 /* extension: `riemann=rusanov`, unknown to the reference's parser (HydroParams.cpp:86-105) */ };
 enum { E2D_ARITH_STRICT = 0, E2D_ARITH_FAST = 1 };
 /* bit mask of faces for e2d_k_make_boundaries */
 enum { E2D_FACES_X = 3, E2D_FACES_YMIN = 4, E2D_FACES_YMAX = 8, E2D_FACES_ALL = 15 };

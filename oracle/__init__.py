@@ -95,6 +95,10 @@ def lib():
                                                C.POINTER(C.c_int)]
         L.e2do_run.argtypes = [pp, dp, dp, C.c_long, dp, C.c_long, dp]
         L.e2do_run.restype = C.c_int
+        L.e2do_riemann_hll.argtypes = [pp, dp, dp, dp]
+        L.e2do_riemann_rusanov.argtypes = [pp, dp, dp, dp]
+        L.e2do_set_flux_solver.argtypes = [C.c_int]
+        L.e2do_get_flux_solver.restype = C.c_int
         _lib = L
     return _lib
 
@@ -151,6 +155,43 @@ def riemann_hllc(p: Params, rec: np.ndarray):
     for k in range(len(rec)):
         lib().e2do_riemann_hllc(C.byref(p), _dp(rec[k, 0:4]), _dp(rec[k, 4:8]), _dp(out[k]))
     return out
+
+
+RIEMANN_APPROX, RIEMANN_HLL, RIEMANN_HLLC, RIEMANN_RUSANOV = 0, 1, 2, 3
+
+
+class flux_solver:
+    """``with oracle.flux_solver(oracle.RIEMANN_APPROX): oracle.run(p)`` — the array operators and ``run`` use that
+    solver instead of the reference's hard-wired riemann_hllc (the product's opt-in ``honourRiemannSolver``)."""
+
+    def __init__(self, solver: int):
+        self.solver = solver
+
+    def __enter__(self):
+        self.prev = lib().e2do_get_flux_solver()
+        lib().e2do_set_flux_solver(self.solver)
+        return self
+
+    def __exit__(self, *exc):
+        lib().e2do_set_flux_solver(self.prev)
+
+
+def _two_state(fn, p: Params, rec: np.ndarray):
+    rec = np.ascontiguousarray(rec, dtype=np.float64).reshape(-1, 8)
+    out = np.zeros((len(rec), 4))
+    for k in range(len(rec)):
+        fn(C.byref(p), _dp(rec[k, 0:4]), _dp(rec[k, 4:8]), _dp(out[k]))
+    return out
+
+
+def riemann_hll(p: Params, rec: np.ndarray):
+    """extension solver (not in the reference): flux of the HLL two-wave solver"""
+    return _two_state(lib().e2do_riemann_hll, p, rec)
+
+
+def riemann_rusanov(p: Params, rec: np.ndarray):
+    """extension solver (not in the reference): Rusanov / local Lax-Friedrichs flux"""
+    return _two_state(lib().e2do_riemann_rusanov, p, rec)
 
 
 def riemann_approx(p: Params, rec: np.ndarray):

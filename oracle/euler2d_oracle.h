@@ -22,7 +22,7 @@ enum { E2DO_FACE_XMIN = 0, E2DO_FACE_XMAX = 1, E2DO_FACE_YMIN = 2, E2DO_FACE_YMA
 enum { E2DO_BC_UNDEFINED = 0, E2DO_BC_DIRICHLET = 1, E2DO_BC_NEUMANN = 2, E2DO_BC_PERIODIC = 3, E2DO_BC_COPY = 4 };
 enum { E2DO_PROBLEM_IMPLODE = 0, E2DO_PROBLEM_BLAST, E2DO_PROBLEM_FOUR_QUADRANT, E2DO_PROBLEM_DISCONTINUITY,
        E2DO_PROBLEM_SHOCKED_BUBBLE };
-enum { E2DO_RIEMANN_APPROX = 0, E2DO_RIEMANN_HLL = 1, E2DO_RIEMANN_HLLC = 2 };
+enum { E2DO_RIEMANN_APPROX = 0, E2DO_RIEMANN_HLL = 1, E2DO_RIEMANN_HLLC = 2, E2DO_RIEMANN_RUSANOV = 3 /* extension */ };
 
 /* field-for-field restatement of HydroParams + HydroSettings + ShockedBubbleParams
  * (src/HydroParams.h:107-265) */
@@ -60,6 +60,12 @@ void e2do_slope_unsplit_hydro_2d(const e2do_params * p, const double q[4], const
 void e2do_trace_unsplit_2d_along_dir(const e2do_params * p, const double q[4], const double dqX[4],
                                      const double dqY[4], double dtdx, double dtdy, int faceId, double qface[4]);
 void e2do_riemann_hllc(const e2do_params * p, const double qleft[4], const double qright[4], double flux[4]);
+/* extension solvers (not in the reference: parity unpinned, see euler2d_oracle.c) and the switch that makes the array
+ * operators / e2do_run use riemann_approx + cmpflx, HLL or Rusanov instead of the reference's hard-wired riemann_hllc */
+void e2do_riemann_hll(const e2do_params * p, const double qleft[4], const double qright[4], double flux[4]);
+void e2do_riemann_rusanov(const e2do_params * p, const double qleft[4], const double qright[4], double flux[4]);
+void e2do_set_flux_solver(int solver);
+int  e2do_get_flux_solver(void);
 void e2do_riemann_approx(const e2do_params * p, const double qleft[4], const double qright[4], double qgdnv[4],
                          double flux[4]);
 void e2do_cmpflx(const e2do_params * p, const double qgdnv[4], double flux[4]);

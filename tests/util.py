@@ -97,7 +97,7 @@ def gpu_eval(hp, func, rec):
 
     nout = {"prim": 5, "slope": 8, "trace": 16, "hllc": 4, "approx": 8, "cmpflx": 4, "hll": 4, "hllc_lean": 5,
             "cell_lean": 6, "trace_lean": 25, "div": 5, "sqrt": 3, "fast_div": 2, "fast_sqrt": 2, "fast_hllc": 4,
-            "fast_cell": 5, "fast_slope": 8, "fast_trace": 16}[func]
+            "fast_cell": 5, "fast_slope": 8, "fast_trace": 16, "rusanov": 4}[func]
     rec = np.ascontiguousarray(rec, dtype=np.float64)
     n = rec.shape[0]
     out = np.zeros((n, nout))
@@ -105,3 +105,52 @@ def gpu_eval(hp, func, rec):
     e2d.check(e2d.lib().e2d_k_eval_host(C.byref(hp.raw), func.encode(), rec.ctypes.data_as(dp),
                                         out.ctypes.data_as(dp), n), "e2d_k_eval_host")
     return out
+
+
+# ------------------------------------------------------------------ Sod shock tube (property tests of the solvers)
+def sod_exact_density(x, t, gamma=1.4, x0=0.5):
+    """Density of the exact solution of Sod's problem (rho, u, p) = (1, 0, 1 | 0.125, 0, 0.1) at time t (Toro, ch. 4:
+    left rarefaction, contact, right shock).  p* is found by Newton iteration on the pressure function."""
+    rl, pl, rr, pr = 1.0, 1.0, 0.125, 0.1
+    cl, cr = np.sqrt(gamma * pl / rl), np.sqrt(gamma * pr / rr)
+    g1, g2 = (gamma - 1) / (2 * gamma), (gamma + 1) / (2 * gamma)
+
+    def f(p, pk, rk, ck):
+        if p > pk:  # shock
+            A, B = 2 / ((gamma + 1) * rk), (gamma - 1) / (gamma + 1) * pk
+            return (p - pk) * np.sqrt(A / (p + B)), np.sqrt(A / (p + B)) * (1 - (p - pk) / (2 * (B + p)))
+        return 2 * ck / (gamma - 1) * ((p / pk) ** g1 - 1), 1 / (rk * ck) * (p / pk) ** (-g2)
+
+    p = 0.5 * (pl + pr)
+    for _ in range(50):
+        fl, dfl = f(p, pl, rl, cl)
+        fr, dfr = f(p, pr, rr, cr)
+        dp = (fl + fr) / (dfl + dfr)
+        p -= dp
+        if abs(dp) < 1e-14:
+            break
+    fl, _ = f(p, pl, rl, cl)
+    fr, _ = f(p, pr, rr, cr)
+    us = 0.5 * (fr - fl)
+    rsl = rl * (p / pl) ** (1 / gamma)                                   # behind the rarefaction
+    rsr = rr * ((p / pr + (gamma - 1) / (gamma + 1)) / ((gamma - 1) / (gamma + 1) * p / pr + 1))  # behind the shock
+    csl = cl * (p / pl) ** g1
+    S = cr * np.sqrt(g2 * p / pr + g1)                                   # shock speed (ur = 0)
+    xi = (x - x0) / t
+    rho = np.where(xi < -cl, rl, 0.0)
+    fan = (xi >= -cl) & (xi < us - csl)
+    rho = np.where(fan, rl * (2 / (gamma + 1) - (gamma - 1) / ((gamma + 1) * cl) * xi) ** (2 / (gamma - 1)), rho)
+    rho = np.where((xi >= us - csl) & (xi < us), rsl, rho)
+    rho = np.where((xi >= us) & (xi < S), rsr, rho)
+    rho = np.where(xi >= S, rr, rho)
+    return rho
+
+
+def sod_initial_state(isize, jsize, nx, gamma=1.4, x0=0.5):
+    """Conservative array [4][jsize][isize] of Sod's problem on [0, 1], uniform in y (ghost cells included)."""
+    x = (np.arange(isize) - 2 + 0.5) / nx
+    left = x < x0
+    U = np.zeros((4, jsize, isize))
+    U[0] = np.where(left, 1.0, 0.125)[None, :]
+    U[1] = (np.where(left, 1.0, 0.1) / (gamma - 1.0))[None, :]
+    return U
