@@ -132,6 +132,22 @@ SIGNATURES = {
     "e2d_save_npy": (C.c_int, [C.c_char_p, _dp, C.c_long]),
     "e2d_enable_timers": (C.c_int, [_vp, C.c_int]),
     "e2d_get_timers": (C.c_int, [_vp, _dp]),
+    "e2d_blast_inside_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]),
+    "e2d_blast_renormalise": (C.c_int, [_vp, C.c_ulonglong]),
+    "e2d_config_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "e2d_config_from_string": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "e2d_config_close": (None, [_vp]),
+    "e2d_config_parse_error": (C.c_int, [_vp]),
+    "e2d_config_get_float": (C.c_float, [_vp, C.c_char_p, C.c_char_p, C.c_float]),
+    "e2d_config_get_integer": (C.c_long, [_vp, C.c_char_p, C.c_char_p, C.c_long]),
+    "e2d_config_get_bool": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_int]),
+    "e2d_config_get_string": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "e2d_config_set_string": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "e2d_params_setup": (C.c_int, [_pp, _vp]),
+    "e2d_profile_enable": (C.c_int, [C.c_int]),
+    "e2d_profile_push": (None, [C.c_char_p]),
+    "e2d_profile_pop": (None, []),
+    "e2d_profile_stats": (C.c_int, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]),
 }
 
 _lib = None

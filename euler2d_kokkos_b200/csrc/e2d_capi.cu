@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost nothing unless a tool is attached
+
 #include "e2d_internal.h"
 
 namespace
@@ -56,6 +58,50 @@ count_launch(int n)
 
 using namespace e2d;
 
+// ---- profiling regions (NVTX): Kokkos::Profiling::pushRegion / popRegion of the reference ----
+namespace
+{
+std::atomic<int>                g_profile{ -1 }; // -1: not decided yet (E2D_PROFILE is read on first use)
+std::atomic<unsigned long long> g_profile_ranges{ 0 };
+thread_local int                t_profile_depth = 0;
+
+bool
+profiling()
+{
+  int v = g_profile.load(std::memory_order_relaxed);
+  if (v < 0)
+  {
+    const char * e = std::getenv("E2D_PROFILE");
+    v = (e && *e && std::strcmp(e, "0") != 0) ? 1 : 0;
+    g_profile.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
+struct ProfileRegion
+{
+  bool on;
+  explicit ProfileRegion(const char * name)
+    : on(profiling())
+  {
+    if (on)
+    {
+      nvtxRangePushA(name);
+      ++t_profile_depth;
+      g_profile_ranges.fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+  ~ProfileRegion()
+  {
+    if (on)
+    {
+      nvtxRangePop();
+      --t_profile_depth;
+    }
+  }
+};
+} // namespace
+
 struct e2d_handle
 {
   e2d_params   p;
@@ -95,6 +141,9 @@ struct e2d_handle
   SlabState *          h_state = nullptr; // pinned mirror
   unsigned long long   seq = 0;           // steps issued through the slab loop so far (flags carry seq)
   bool                 seq_poisoned = false; // a wait for a peer timed out: flags and state are no longer trustworthy
+  // Sedov init on a slab: disc cells of the rows this rank owns; the state is unusable until e2d_blast_renormalise
+  unsigned long long   blast_inside_local = 0;
+  bool                 blast_pending = false;
   struct
   {
     bool       connected = false;
@@ -223,7 +272,8 @@ godunov_impl(e2d_handle * h, double * in, double * out, double dt, bool do_bc)
 
   if (do_bc)
   {
-    PhaseTimer tb(h, 0);
+    ProfileRegion pr("make_boundaries"); // :294
+    PhaseTimer    tb(h, 0);
     E2D_CUDA(launch_make_boundaries(p, h->g, in, faces_for(h), nullptr, st)); // :296
   }
   const int  impl = p.implementationVersion;
@@ -244,9 +294,11 @@ godunov_impl(e2d_handle * h, double * in, double * out, double dt, bool do_bc)
     unsigned long long * cfl = h->cfl_cache_ok ? h->d_cfl + w_out : nullptr;
     if (cfl)
       E2D_CUDA(cudaMemsetAsync(cfl, 0, sizeof(unsigned long long), st));
+    ProfileRegion pi(impl == 0 ? "hydro_impl0" : (impl == 1 ? "hydro_impl1" : "hydro_impl2")); // :315,:335,:357
     if (impl == 0)
     {
-      PhaseTimer tf(h, 3); // the reference times its flux kernel for implementation 0 only (:316-320)
+      ProfileRegion pf("compute_fluxes"); // :317 (the fused kernel: primitives, fluxes and update in one launch)
+      PhaseTimer    tf(h, 3); // the reference times its flux kernel for implementation 0 only (:316-320)
       E2D_CUDA(launch_fused_step(p, h->g, in, out, dt, nullptr, cfl, nullptr, st));
     }
     else
@@ -258,22 +310,27 @@ godunov_impl(e2d_handle * h, double * in, double * out, double dt, bool do_bc)
   }
   E2D_CUDA(cudaMemcpyAsync(out, in, h->n * sizeof(double), cudaMemcpyDeviceToDevice, st)); // :302
   {
-    PhaseTimer tp(h, 2);
+    ProfileRegion pp("compute_primitives"); // :308
+    PhaseTimer    tp(h, 2);
     E2D_CUDA(launch_convert_to_primitives(p, h->g, in, h->Q, st)); // :309
   }
   if (impl == 0)
   {
+    ProfileRegion pi("hydro_impl0"); // :315
     {
-      PhaseTimer tf(h, 3);
+      ProfileRegion pf("compute_fluxes"); // :317
+      PhaseTimer    tf(h, 3);
       E2D_CUDA(launch_compute_and_store_fluxes(p, h->g, h->Q, h->Fx, h->Fy, dtdx, dtdy, st)); // :319
     }
     {
-      PhaseTimer tu(h, 4);
+      ProfileRegion pu("update_hydro"); // :324
+      PhaseTimer    tu(h, 4);
       E2D_CUDA(launch_update(p, h->g, out, h->Fx, h->Fy, st)); // :326
     }
   }
   else
   { // :338-352
+    ProfileRegion pi("hydro_impl1"); // :335
     E2D_CUDA(launch_compute_slopes(p, h->g, h->Q, h->Sx, h->Sy, st));
     E2D_CUDA(launch_trace_and_fluxes(p, h->g, h->Q, h->Sx, h->Sy, h->Fx, dtdx, dtdy, 1, st));
     E2D_CUDA(launch_update_dir(p, h->g, out, h->Fx, 1, st));
@@ -614,15 +671,22 @@ extern "C"
         rc = fail(E2D_ERR_UNSUPPORTED, "y-slabs need boundary_type_ymin and boundary_type_ymax both periodic or neither");
         break;
       }
+      (void)refined_reciprocal(p->dx); // warm the cache: launches inside the loops must never synchronise
+      (void)refined_reciprocal(p->dy);
       // HydroRun.h:185-214: initial condition, then U2 = U
       if (p->problemType == E2D_PROBLEM_BLAST && p->blast_total_energy_inside > 0 && !h->whole)
       {
-        rc = fail(E2D_ERR_UNSUPPORTED, "energy-renormalised blast init needs the whole domain on one device");
-        break;
+        // Sedov on slabs: the energy inside the disc is E_tot / (volume of ALL disc cells), a reduction over the whole
+        // grid in the reference (src/HydroRunFunctors.h:1445-1463).  This rank counts the disc cells of the rows it
+        // owns; the initialisation is completed by e2d_blast_renormalise with the sum over the ranks (an integer
+        // all-reduce: PeerSlabRun does it, e2d_peer_connect_local does it for handles of one process).
+        const int jlo = h->slab.rank == 0 ? 0 : 2;
+        const int jhi = h->slab.rank == h->slab.nranks - 1 ? jsize_loc : jsize_loc - 2;
+        E2D_TRY(launch_init_problem(*p, h->g, h->U, h->stream, &h->blast_inside_local, -1, jlo, jhi));
+        h->blast_pending = true;
       }
-      (void)refined_reciprocal(p->dx); // warm the cache: launches inside the loops must never synchronise
-      (void)refined_reciprocal(p->dy);
-      E2D_TRY(launch_init_problem(*p, h->g, h->U, h->stream));
+      else
+        E2D_TRY(launch_init_problem(*p, h->g, h->U, h->stream));
       E2D_TRY(cudaMemcpyAsync(h->U2, h->U, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
       E2D_TRY(cudaStreamSynchronize(h->stream));
 #undef E2D_TRY
@@ -698,11 +762,46 @@ extern "C"
   }
 
   int
+  e2d_blast_inside_count(e2d_handle * h, unsigned long long * n_local, int * pending)
+  {
+    if (!h || !n_local)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    *n_local = h->blast_inside_local;
+    if (pending)
+      *pending = h->blast_pending ? 1 : 0;
+    return E2D_OK;
+  }
+
+  int
+  e2d_blast_renormalise(e2d_handle * h, unsigned long long n_inside_global)
+  {
+    if (!h)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    if (!h->blast_pending)
+      return E2D_OK; // nothing to complete (whole domain, or not the Sedov problem)
+    if (n_inside_global < h->blast_inside_local)
+      return fail(E2D_ERR_INVALID, "the global count of disc cells cannot be smaller than this slab's own");
+    cudaSetDevice(h->device);
+    E2D_CUDA(launch_init_problem(h->p, h->g, h->U, h->stream, nullptr, (long long)n_inside_global));
+    E2D_CUDA(cudaMemcpyAsync(h->U2, h->U, h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    E2D_CUDA(cudaStreamSynchronize(h->stream));
+    h->blast_pending = false;
+    return E2D_OK;
+  }
+
+#define E2D_REFUSE_PENDING(h)                                                                                         \
+  if ((h)->blast_pending)                                                                                             \
+    return fail(E2D_ERR_INVALID, "Sedov initialisation of this slab is incomplete: call e2d_blast_renormalise with the " \
+                                 "disc-cell count summed over all ranks (e2d_blast_inside_count)")
+
+  int
   e2d_compute_dt(e2d_handle * h, int useU, double * dt, double * invdt_local)
   {
     if (!h || !dt)
       return fail(E2D_ERR_INVALID, "bad argument");
+    E2D_REFUSE_PENDING(h);
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
+    ProfileRegion  pr("compute_dt");               // HydroRun.h:242
     const double * A = (useU == 0) ? h->U : h->U2; // HydroRun.h:237-240
     const int      w = (useU == 0) ? 0 : 1;
     double         invDt = 0.0;
@@ -727,6 +826,7 @@ extern "C"
     if (!h || (which != E2D_U && which != E2D_U2))
       return fail(E2D_ERR_INVALID, "bad argument");
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
+    ProfileRegion pr("make_boundaries");
     E2D_CUDA(launch_make_boundaries(h->p, h->g, array_of(h, which), faces_for(h), nullptr, h->stream));
     return E2D_OK;
   }
@@ -736,6 +836,7 @@ extern "C"
   {
     if (!h)
       return fail(E2D_ERR_INVALID, "bad argument");
+    E2D_REFUSE_PENDING(h);
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
     h->loop_primed = false;
     if (nStep % 2 == 0) // HydroRun.h:263-270
@@ -790,6 +891,7 @@ extern "C"
     const int nranks = h->slab.nranks, rank = h->slab.rank;
     if (nranks > 1 && !h->peers.connected)
       return fail(E2D_ERR_UNSUPPORTED, "e2d_run on a slab needs its peers: call e2d_ipc_connect / e2d_peer_connect_local");
+    E2D_REFUSE_PENDING(h);
     const e2d_params & p = h->p;
     cudaStream_t       st = h->stream;
     E2D_CUDA(cudaSetDevice(h->device));
@@ -888,6 +990,7 @@ extern "C"
     so.bc_ymin = p.boundary_type_ymin;
     so.bc_ymax = p.boundary_type_ymax;
 
+    ProfileRegion pr_loop("main_loop"); // src/main.cpp:93 — the whole loop is this one call here
     E2D_CUDA(cudaEventRecord(h->ev[0], st));
     int       n_host = h->nStep; // parity the host believes in; wrong only after `done`, when the step is a no-op
     const int batch = 64;
@@ -1125,6 +1228,19 @@ extern "C"
     for (int r = 0; r < n; ++r)
       if (!hs[r] || hs[r]->slab.rank != r || hs[r]->slab.nranks != n)
         return fail(E2D_ERR_INVALID, "handles must be the n slabs of one run, in rank order");
+    { // Sedov on slabs of one process: the integer "all-reduce" of the disc-cell counts is a loop
+      unsigned long long total = 0;
+      bool               pending = false;
+      for (int r = 0; r < n; ++r)
+      {
+        total += hs[r]->blast_inside_local;
+        pending = pending || hs[r]->blast_pending;
+      }
+      if (pending)
+        for (int r = 0; r < n; ++r)
+          if (int rc = e2d_blast_renormalise(hs[r], total))
+            return rc;
+    }
     for (int r = 0; r < n; ++r)
     {
       e2d_handle * h = hs[r];
@@ -1820,6 +1936,42 @@ extern "C"
     if (int rc = e2d_save_npy((d + "sedov_blast_radial_distances.npy").c_str(), dist.data(), nbins)) // :134
       return rc;
     return e2d_save_npy((d + "sedov_blast_density_profile.npy").c_str(), sums.data(), nbins); // :135
+  }
+
+  int
+  e2d_profile_enable(int on)
+  {
+    g_profile.store(on ? 1 : 0, std::memory_order_relaxed);
+    return E2D_OK;
+  }
+
+  void
+  e2d_profile_push(const char * name)
+  {
+    if (!profiling())
+      return;
+    nvtxRangePushA(name ? name : "");
+    ++t_profile_depth;
+    g_profile_ranges.fetch_add(1, std::memory_order_relaxed);
+  }
+
+  void
+  e2d_profile_pop(void)
+  {
+    if (!profiling() || t_profile_depth <= 0)
+      return;
+    nvtxRangePop();
+    --t_profile_depth;
+  }
+
+  int
+  e2d_profile_stats(unsigned long long * ranges_opened, int * depth)
+  {
+    if (ranges_opened)
+      *ranges_opened = g_profile_ranges.load(std::memory_order_relaxed);
+    if (depth)
+      *depth = t_profile_depth;
+    return profiling() ? 1 : 0;
   }
 
   int

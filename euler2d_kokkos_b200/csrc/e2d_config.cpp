@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <new>
 #include <sstream>
 #include <string>
 
@@ -296,6 +297,120 @@ e2d_params_init(e2d_params * p)
   p->smallp = p->smallc * p->smallc / p->gamma0;
   p->smallpp = p->smallr * p->smallp;
   p->gamma6 = (p->gamma0 + 1.0) / (2.0 * p->gamma0);
+  return E2D_OK;
+}
+
+// ---- ConfigMap over the C ABI (config/ConfigMap.h:26-46, config/inih/INIReader.h) ----
+struct e2d_config
+{
+  Config cfg;
+  int    parse_error = 0; // INIReader::ParseError(): -1 when the file could not be opened
+};
+
+extern "C" int
+e2d_config_open(const char * path, e2d_config ** out)
+{
+  if (!path || !out)
+    return E2D_ERR_INVALID;
+  e2d_config * c = new (std::nothrow) e2d_config();
+  if (!c)
+    return E2D_ERR_ALLOC;
+  FILE * f = std::fopen(path, "r");
+  if (f)
+  {
+    parse_ini([f](char * buf, int n) { return std::fgets(buf, n, f) != nullptr; }, c->cfg.kv);
+    std::fclose(f);
+  }
+  else
+    c->parse_error = -1;
+  *out = c;
+  return f ? E2D_OK : E2D_ERR_IO; // the handle is valid either way (an empty map), like the reference's object
+}
+
+extern "C" int
+e2d_config_from_string(const char * ini_text, e2d_config ** out)
+{
+  if (!ini_text || !out)
+    return E2D_ERR_INVALID;
+  e2d_config * c = new (std::nothrow) e2d_config();
+  if (!c)
+    return E2D_ERR_ALLOC;
+  const char * cur = ini_text;
+  parse_ini(
+    [&cur](char * buf, int n) {
+      if (!*cur)
+        return false;
+      int k = 0;
+      while (k < n - 1 && *cur)
+      {
+        buf[k++] = *cur;
+        if (*cur++ == '\n')
+          break;
+      }
+      buf[k] = '\0';
+      return true;
+    },
+    c->cfg.kv);
+  *out = c;
+  return E2D_OK;
+}
+
+extern "C" void
+e2d_config_close(e2d_config * c)
+{
+  delete c;
+}
+
+extern "C" int
+e2d_config_parse_error(const e2d_config * c)
+{
+  return c ? c->parse_error : -1;
+}
+
+extern "C" float
+e2d_config_get_float(const e2d_config * c, const char * section, const char * name, float dflt)
+{
+  return (c && section && name) ? c->cfg.real(section, name, dflt) : dflt;
+}
+
+extern "C" long
+e2d_config_get_integer(const e2d_config * c, const char * section, const char * name, long dflt)
+{
+  return (c && section && name) ? c->cfg.integer(section, name, dflt) : dflt;
+}
+
+extern "C" int
+e2d_config_get_bool(const e2d_config * c, const char * section, const char * name, int dflt)
+{
+  return (c && section && name) ? (c->cfg.boolean(section, name, dflt != 0) ? 1 : 0) : dflt;
+}
+
+extern "C" int
+e2d_config_get_string(const e2d_config * c, const char * section, const char * name, const char * dflt, char * buf,
+                      size_t cap)
+{
+  if (!buf || cap == 0)
+    return E2D_ERR_INVALID;
+  const std::string v = (c && section && name) ? c->cfg.string(section, name, dflt ? dflt : "") : std::string(dflt ? dflt : "");
+  std::snprintf(buf, cap, "%s", v.c_str());
+  return E2D_OK;
+}
+
+extern "C" int
+e2d_config_set_string(e2d_config * c, const char * section, const char * name, const char * value)
+{
+  if (!c || !section || !name || !value)
+    return E2D_ERR_INVALID;
+  c->cfg.kv[make_key(section, name)] = value;
+  return E2D_OK;
+}
+
+extern "C" int
+e2d_params_setup(e2d_params * out, const e2d_config * c)
+{
+  if (!out || !c)
+    return E2D_ERR_INVALID;
+  setup(c->cfg, out);
   return E2D_OK;
 }
 

@@ -126,7 +126,12 @@ Settings make_settings(const e2d_params & p);
 Geom     make_geom(const e2d_params & p, int jsize_loc, int j_off);
 
 // every launcher returns cudaGetLastError() after the launch
-cudaError_t launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream_t st);
+// Sedov (blast with total_energy_inside > 0): n_inside_out != nullptr -> only count the disc cells of the local rows
+// [count_jlo, count_jhi) and return (the energy is NOT renormalised yet); n_inside_given >= 0 -> renormalise with that
+// global count; neither -> count and renormalise in one call (whole domain).
+cudaError_t launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream_t st,
+                                unsigned long long * n_inside_out = nullptr, long long n_inside_given = -1,
+                                int count_jlo = 0, int count_jhi = 0);
 cudaError_t launch_make_boundaries(const e2d_params & p, const Geom & g, double * U, int faces, const int * d_done,
                                    cudaStream_t st);
 cudaError_t launch_reduce_invdt(const e2d_params & p, const Geom & g, const double * U, unsigned long long * d_bits,

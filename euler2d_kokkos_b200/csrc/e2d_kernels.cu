@@ -99,7 +99,8 @@ struct InitArgs
 };
 
 __global__ void __launch_bounds__(128)
-k_init_problem(Geom g, InitArgs a, double * __restrict__ U, unsigned long long * __restrict__ n_inside)
+k_init_problem(Geom g, InitArgs a, double * __restrict__ U, unsigned long long * __restrict__ n_inside, int count_jlo,
+               int count_jhi)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = grid_row();
@@ -119,7 +120,7 @@ k_init_problem(Geom g, InitArgs a, double * __restrict__ U, unsigned long long *
     {
       u[ID] = a.blast_density_in;
       u[IP] = a.blast_pressure_in / (a.gamma0 - 1.0);
-      if (n_inside)
+      if (n_inside && j >= count_jlo && j < count_jhi) // a slab counts the rows it owns (no halo row twice)
         atomicAdd(n_inside, 1ull);
       if (a.blast_energy_density >= 0.0)
         u[IP] = a.blast_energy_density;
@@ -1066,7 +1067,8 @@ grid_rows(int ncols, int nrows, int block)
 }
 
 cudaError_t
-launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream_t st)
+launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream_t st, unsigned long long * n_inside_out,
+                    long long n_inside_given, int count_jlo, int count_jhi)
 {
   InitArgs a;
   a.problem = p.problemType;
@@ -1096,29 +1098,43 @@ launch_init_problem(const e2d_params & p, const Geom & g, double * U, cudaStream
   a.shock_loc = p.shock_loc;
 
   const dim3 grid = grid_rows(g.isize, g.jsize, 128);
+  if (count_jhi <= 0)
+    count_jhi = g.jsize;
   if (p.problemType == E2D_PROBLEM_BLAST && p.blast_total_energy_inside > 0)
   {
     // Sedov variant (:1445-1463): count the cells inside the disc, form the volume the way a serial
     // Kokkos::Sum would (repeated += dx*dy), then overwrite the energy inside with E_tot / volume.
-    unsigned long long * d_n = nullptr;
-    cudaError_t          e = cudaMalloc(&d_n, sizeof(unsigned long long));
-    if (e != cudaSuccess)
-      return e;
-    cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st);
-    k_init_problem<<<grid, 128, 0, st>>>(g, a, U, d_n);
-    count_launch();
+    // A slab counts its own rows and hands the number out (n_inside_out); the caller sums over the ranks and comes
+    // back with the global count (n_inside_given >= 0): integers, hence exact and order independent.
     unsigned long long n_inside = 0;
-    cudaMemcpyAsync(&n_inside, d_n, sizeof n_inside, cudaMemcpyDeviceToHost, st);
-    e = cudaStreamSynchronize(st);
-    cudaFree(d_n);
-    if (e != cudaSuccess)
-      return e;
+    if (n_inside_given >= 0)
+      n_inside = (unsigned long long)n_inside_given;
+    else
+    {
+      unsigned long long * d_n = nullptr;
+      cudaError_t          e = cudaMalloc(&d_n, sizeof(unsigned long long));
+      if (e != cudaSuccess)
+        return e;
+      cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st);
+      k_init_problem<<<grid, 128, 0, st>>>(g, a, U, d_n, count_jlo, count_jhi);
+      count_launch();
+      cudaMemcpyAsync(&n_inside, d_n, sizeof n_inside, cudaMemcpyDeviceToHost, st);
+      e = cudaStreamSynchronize(st);
+      cudaFree(d_n);
+      if (e != cudaSuccess)
+        return e;
+      if (n_inside_out)
+      { // the caller completes the initialisation once it knows the global count
+        *n_inside_out = n_inside;
+        return cudaGetLastError();
+      }
+    }
     double volume = 0.0;
     for (unsigned long long k = 0; k < n_inside; ++k)
       volume += p.dx * p.dy;
     a.blast_energy_density = p.blast_total_energy_inside / volume;
   }
-  k_init_problem<<<grid, 128, 0, st>>>(g, a, U, nullptr);
+  k_init_problem<<<grid, 128, 0, st>>>(g, a, U, nullptr, 0, 0);
   count_launch();
   return cudaGetLastError();
 }

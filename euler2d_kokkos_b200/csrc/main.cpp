@@ -41,15 +41,19 @@ main(int argc, char * argv[])
   real_t t = 0, dt = 0;
   int    nStep = 0;
 
-  HydroParams params;
-  params.setup(ini);
+  // the reference's sequence, verbatim (src/main.cpp:76-86)
+  ConfigMap   configMap(ini);
+  HydroParams params = HydroParams();
+  params.setup(configMap);
   params.print();
 
-  HydroRun * hydro = new HydroRun(params, /*timers=*/!device_loop);
+  using device = void;
+  HydroRun<device> * hydro = new HydroRun<device>(params, configMap, /*timers=*/!device_loop);
   dt = hydro->compute_dt(nStep % 2);
   hydro->make_boundaries(hydro->U);
   hydro->make_boundaries(hydro->U2);
 
+  e2d_profile_push("main_loop"); // Kokkos::Profiling::pushRegion("main_loop"), main.cpp:93 (NVTX, with E2D_PROFILE=1)
   std::cout << "Start computation....\n";
   double     t_io = 0, t_dt = 0;
   const auto t0 = std::chrono::steady_clock::now();
@@ -99,10 +103,11 @@ main(int argc, char * argv[])
   }
   hydro->synchronize();
   const double t_tot = secs_since(t0);
+  e2d_profile_pop();
 
   // post-processing for Sedov blast (src/main.cpp:175-179: always hydro->U, whatever the parity of nStep)
   if (params.problemType == E2D_PROBLEM_BLAST && params.blast_total_energy_inside > 0)
-    euler2d_b200::ComputeRadialProfileFunctor::apply(params, *hydro, hydro->U);
+    euler2d_b200::ComputeRadialProfileFunctor<device>::apply(params, hydro->U);
 
   const double t_comp = hydro->godunov_timer.elapsed(), t_prim = hydro->compute_primitive_timer.elapsed();
   const double t_flux = hydro->comp_fluxes_timer.elapsed(), t_update = hydro->update_hydro_timer.elapsed();

@@ -128,6 +128,14 @@ class PeerSlabRun:
         slab = Slab(self.rank, self.world, self.geo.ny_loc, self.geo.j_off)
         self.hydro = HydroRun(params, slab=slab)
         if self.world > 1:
+            # Sedov init: the disc-cell counts of the slabs are summed (integer all-reduce) and every rank completes
+            # its initialisation with the global count (e2d_blast_renormalise; a no-op for every other problem)
+            n_loc, pending = C.c_ulonglong(), C.c_int()
+            check(lib().e2d_blast_inside_count(self.hydro._h, C.byref(n_loc), C.byref(pending)), "e2d_blast_inside_count")
+            cnt = torch.tensor([n_loc.value, pending.value], dtype=torch.int64, device=self.device)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
+            if int(cnt[1].item()) > 0:
+                check(lib().e2d_blast_renormalise(self.hydro._h, int(cnt[0].item())), "e2d_blast_renormalise")
             blob = _lib.IpcBlob()
             check(lib().e2d_ipc_export(self.hydro._h, C.byref(blob)), "e2d_ipc_export")
             mine = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).to(self.device)

@@ -18,6 +18,50 @@ from . import _lib
 from ._lib import E2D_U, E2D_U2, E2D_Q, LAYOUT_SOA, LAYOUT_KOKKOS_OMP, Params, RunStats, Slab, check, lib
 
 
+class ConfigMap:
+    """config/ConfigMap.h:26-46 — the parsed .ini as a key/value map with the reference's typed getters."""
+
+    def __init__(self, filename: str | None = None, text: str | None = None):
+        self._c = C.c_void_p()
+        if text is not None:
+            check(lib().e2d_config_from_string(text.encode(), C.byref(self._c)), "e2d_config_from_string")
+        else:
+            lib().e2d_config_open(os.fsencode(filename or ""), C.byref(self._c))  # a missing file gives an empty map
+
+    def __del__(self):
+        try:
+            if self._c:
+                lib().e2d_config_close(self._c)
+                self._c = C.c_void_p()
+        except Exception:
+            pass
+
+    def ParseError(self) -> int:
+        return lib().e2d_config_parse_error(self._c)
+
+    def getFloat(self, section: str, name: str, default_value: float) -> float:
+        return lib().e2d_config_get_float(self._c, section.encode(), name.encode(), default_value)
+
+    def getInteger(self, section: str, name: str, default_value: int) -> int:
+        return lib().e2d_config_get_integer(self._c, section.encode(), name.encode(), default_value)
+
+    def getBool(self, section: str, name: str, default_value: bool) -> bool:
+        return bool(lib().e2d_config_get_bool(self._c, section.encode(), name.encode(), int(default_value)))
+
+    def getString(self, section: str, name: str, default_value: str) -> str:
+        buf = C.create_string_buffer(512)
+        lib().e2d_config_get_string(self._c, section.encode(), name.encode(), default_value.encode(), buf, 512)
+        return buf.value.decode()
+
+    def setString(self, section: str, name: str, value) -> None:
+        check(lib().e2d_config_set_string(self._c, section.encode(), name.encode(), str(value).encode()))
+
+    setFloat = setInteger = setString
+
+    def setBool(self, section: str, name: str, value: bool) -> None:
+        self.setString(section, name, "true" if value else "false")
+
+
 class HydroParams:
     """Parameters read from an .ini with the reference's semantics (floats go through strtof)."""
 
@@ -39,9 +83,12 @@ class HydroParams:
         check(lib().e2d_params_from_string(text.encode(), C.byref(p)), "e2d_params_from_string")
         return cls(p)
 
-    def setup(self, ini_path: str) -> None:  # HydroParams::setup(ConfigMap&)
+    def setup(self, configMap) -> None:  # HydroParams::setup(ConfigMap&); a path is accepted too
         p = Params()
-        check(lib().e2d_params_from_ini(ini_path.encode(), C.byref(p)), "e2d_params_from_ini")
+        if isinstance(configMap, ConfigMap):
+            check(lib().e2d_params_setup(C.byref(p), configMap._c), "e2d_params_setup")
+        else:
+            check(lib().e2d_params_from_ini(os.fsencode(configMap), C.byref(p)), "e2d_params_from_ini")
         object.__setattr__(self, "raw", p)
 
     def init(self) -> None:  # HydroParams::init()
@@ -75,8 +122,11 @@ class HydroRun:
     U2 = E2D_U2
     Q = E2D_Q
 
-    def __init__(self, params: HydroParams, slab: Slab | None = None, stream: int | None = None,
-                 U_ptr: int | None = None, U2_ptr: int | None = None):
+    def __init__(self, params: HydroParams, configMap: "ConfigMap | None" = None, slab: Slab | None = None,
+                 stream: int | None = None, U_ptr: int | None = None, U2_ptr: int | None = None):
+        """HydroRun(params, configMap) as in src/HydroRun.h:143 (the map is only read through params here)."""
+        if isinstance(configMap, Slab):  # older call order HydroRun(params, slab)
+            configMap, slab = None, configMap
         self.params = params
         self._h = C.c_void_p()
         check(lib().e2d_create(C.byref(params.raw), C.byref(slab) if slab is not None else None,
@@ -225,11 +275,13 @@ def main_loop(ini_path: str, verbose: bool = True, device_loop: bool = False):
     """The program of src/main.cpp:76-204 through the HydroRun mirror. Returns (hydro, nStep, t)."""
     import time
 
-    params = HydroParams.from_ini(ini_path)
+    configMap = ConfigMap(ini_path)          # main.cpp:76-86
+    params = HydroParams()
+    params.setup(configMap)
     if verbose:
         print(f"Using Euler implementation version {params.implementationVersion}")
         params.print()
-    hydro = HydroRun(params)
+    hydro = HydroRun(params, configMap)
     t, nStep = 0.0, 0
     dt = hydro.compute_dt(nStep % 2)          # main.cpp:87
     hydro.make_boundaries(HydroRun.U)         # main.cpp:90-91

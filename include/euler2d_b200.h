@@ -117,6 +117,25 @@ unsigned long long e2d_kernel_launch_count(void);
 int e2d_params_from_ini(const char * path, e2d_params * out);
 /* same, from an in-memory .ini text (used by tests and by callers that build decks on the fly) */
 int e2d_params_from_string(const char * ini_text, e2d_params * out);
+/* ConfigMap (config/ConfigMap.h:26-46 over config/inih/INIReader.h): the parsed .ini as a key/value map with the
+ * reference's typed getters — getFloat goes through strtof (ConfigMap.cpp:32-40), integers through strtol base 0,
+ * booleans accept 1/yes/true/on and 0/no/false/off; keys are "section.name", lower-cased; the last assignment wins.
+ * e2d_config_open returns E2D_ERR_IO for a missing file but still hands out a valid (empty) map, because the
+ * reference never checks ParseError() (src/main.cpp:76). */
+typedef struct e2d_config e2d_config;
+int   e2d_config_open(const char * path, e2d_config ** out);
+int   e2d_config_from_string(const char * ini_text, e2d_config ** out);
+void  e2d_config_close(e2d_config * c);
+int   e2d_config_parse_error(const e2d_config * c); /* INIReader::ParseError(): 0, or -1 when the file did not open */
+float e2d_config_get_float(const e2d_config * c, const char * section, const char * name, float default_value);
+long  e2d_config_get_integer(const e2d_config * c, const char * section, const char * name, long default_value);
+int   e2d_config_get_bool(const e2d_config * c, const char * section, const char * name, int default_value);
+int   e2d_config_get_string(const e2d_config * c, const char * section, const char * name, const char * default_value,
+                            char * buf, size_t cap);
+/* ConfigMap::setFloat / setBool and friends: values are stored as text, like the reference's map */
+int   e2d_config_set_string(e2d_config * c, const char * section, const char * name, const char * value);
+/* HydroParams::setup(ConfigMap &) (src/HydroParams.cpp:43-155), including init() */
+int   e2d_params_setup(e2d_params * out, const e2d_config * c);
 /* recompute the derived fields after editing nx/ny/xmin/... (HydroParams::init, :161-190) */
 int e2d_params_init(e2d_params * p);
 /* HydroParams::print (src/HydroParams.cpp:196-224), same text, to stdout */
@@ -213,6 +232,15 @@ typedef struct e2d_slab
 int e2d_create(const e2d_params * p, const e2d_slab * slab, double * U_ext, double * U2_ext, void * stream,
                e2d_handle ** out);
 int e2d_destroy(e2d_handle * h);
+
+/* Sedov blast (problem=blast with total_energy_inside > 0) on y-slabs.  InitBlastFunctor::apply
+ * (src/HydroRunFunctors.h:1445-1463) sets the energy inside the disc to E_tot / volume_inside, where volume_inside is
+ * a Kokkos::Sum over the WHOLE grid.  e2d_create on a slab counts the disc cells of the rows the rank owns and leaves
+ * the handle "pending": every compute entry point refuses it until e2d_blast_renormalise is given the count summed
+ * over all ranks (an integer all-reduce, hence exact and identical to the single-domain value).  PeerSlabRun does that
+ * with torch.distributed; e2d_peer_connect_local does it for the handles of one process.  No-ops otherwise. */
+int e2d_blast_inside_count(e2d_handle * h, unsigned long long * n_local, int * pending /* may be NULL */);
+int e2d_blast_renormalise(e2d_handle * h, unsigned long long n_inside_global);
 
 /* HydroRun::compute_dt(useU) (src/HydroRun.h:229-251): *dt = cfl / max(invDt). Synchronous.
  * On a slab, *invdt_local (may be NULL) returns this rank's partial max so the caller can
@@ -332,6 +360,17 @@ int e2d_save_npy(const char * path, const double * data, long n);
  * e2d_godunov_unsplit path when timing is enabled: [boundaries, godunov, primitive, fluxes, update] */
 int e2d_enable_timers(e2d_handle * h, int on);
 int e2d_get_timers(e2d_handle * h, double out[5]);
+
+/* Profiling regions: Kokkos::Profiling::pushRegion / popRegion (src/HydroRun.h:242-360, src/main.cpp:93,111) as
+ * named NVTX ranges.  Off by default; on with e2d_profile_enable(1) or the environment variable E2D_PROFILE=1 (read
+ * once).  In profile mode the library wraps its own phases with the reference's region names — compute_dt,
+ * make_boundaries, compute_primitives, hydro_impl0 (compute_fluxes, update_hydro nested inside), hydro_impl1,
+ * hydro_impl2 — and a host program can add its own (main_loop, output) through push / pop.  e2d_profile_stats
+ * reports how many ranges were opened and the current nesting depth (tests; a balanced program ends at depth 0). */
+int  e2d_profile_enable(int on);
+void e2d_profile_push(const char * name);
+void e2d_profile_pop(void);
+int  e2d_profile_stats(unsigned long long * ranges_opened, int * depth);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,2 @@
+// src/real_type.h of the reference, served by the B200 library (everything lives in HydroRun.hpp).
+#include "HydroRun.h"

@@ -345,6 +345,37 @@ def test_peer_slab_loop_matches_oracle_bitwise(deck, ov, nslabs):
     assert_bitwise(U, U_ref[INNER], f"{deck} {nslabs} slabs")
 
 
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_sedov_renormalised_init_on_slabs(nslabs):
+    """problem=blast with total_energy_inside: the energy inside the disc is E_tot / (volume of all disc cells), a
+    reduction over the whole grid in the reference (src/HydroRunFunctors.h:1445-1463).  Slabs count their own rows and
+    complete the initialisation with the integer sum over the ranks: bit-identical to the single domain, disc cut by the
+    slab interfaces included."""
+    hp, op = both_params("sedov_blast_2d", mesh__nx=96, mesh__ny=90, blast__radius=0.2, run__nOutput=-1)
+    steps = 30
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, steps)
+    U, st, dts = run_peer_slabs(hp, nslabs, steps)
+    assert st.nStep == n_ref and st.t == t_ref
+    assert_bitwise(dts, dts_ref[1:], "dt history")
+    assert_bitwise(U, U_ref[INNER], f"sedov on {nslabs} slabs")
+
+
+def test_sedov_slab_is_refused_until_the_global_count_is_known():
+    import ctypes as C
+
+    from euler2d_kokkos_b200 import Slab
+
+    hp, _ = both_params("sedov_blast_2d", mesh__nx=64, mesh__ny=64, blast__radius=0.2, run__nOutput=-1)
+    with HydroRun(hp, slab=Slab(0, 2, 32, 0)) as h:
+        n, pending = C.c_ulonglong(), C.c_int()
+        e2d.check(e2d.lib().e2d_blast_inside_count(h._h, C.byref(n), C.byref(pending)))
+        assert pending.value == 1 and n.value > 0
+        with pytest.raises(e2d.E2dError, match="Sedov"):
+            h.compute_dt(0)
+        e2d.check(e2d.lib().e2d_blast_renormalise(h._h, 2 * n.value))
+        assert h.compute_dt(0) > 0
+
+
 def test_peer_slab_loop_stops_on_tend_on_every_rank():
     hp, op = both_params("four_quadrant", mesh__nx=48, mesh__ny=48, run__nOutput=-1)
     U_ref, dts_ref, n_ref, t_ref = oracle.run(op)

@@ -169,3 +169,96 @@ def test_save_npy_matches_cnpy_bytes(tmp_path):
     mine = tmp_path / "mine.npy"
     assert e2d.lib().e2d_save_npy(os.fsencode(str(mine)), d.ctypes.data_as(C.POINTER(C.c_double)), d.size) == 0
     assert open(mine, "rb").read() == ref_bytes
+
+
+def test_configmap_typed_getters_follow_the_reference():
+    """config/ConfigMap.cpp:32-74 + config/inih/INIReader.cpp: floats through strtof, integers through strtol base 0,
+    booleans from the words the reference accepts, keys case-insensitive, last assignment wins, defaults otherwise."""
+    import numpy as np
+
+    from euler2d_kokkos_b200 import ConfigMap, HydroParams
+
+    text = "[hydro]\ngamma0=1.666\ncfl = 0.8 ; trailing comment\nniter_riemann=0x10\n[RUN]\ntEnd=0.1\ntend=0.25\n" \
+           "[output]\noutputPrefix=abc\n[other]\nflag=yes\nnoflag=off\n"
+    cm = ConfigMap(text=text)
+    assert cm.getFloat("hydro", "gamma0", 0.0) == float(np.float32(1.666))
+    assert cm.getFloat("hydro", "cfl", 0.0) == float(np.float32(0.8))
+    assert cm.getInteger("hydro", "niter_riemann", 3) == 16
+    assert cm.getFloat("run", "tEnd", 0.0) == 0.25 and cm.getFloat("RUN", "TEND", 0.0) == 0.25
+    assert cm.getString("output", "outputPrefix", "output") == "abc"
+    assert cm.getString("output", "outputDir", "./") == "./"
+    assert cm.getBool("other", "flag", False) is True and cm.getBool("other", "noflag", True) is False
+    assert cm.getBool("other", "absent", True) is True and cm.getFloat("nope", "x", 2.5) == 2.5
+    cm.setFloat("mesh", "nx", 48)
+    cm.setBool("other", "flag", False)
+    assert cm.getInteger("mesh", "nx", 0) == 48 and cm.getBool("other", "flag", True) is False
+    # HydroParams::setup(ConfigMap&) == the path-based reader
+    a, b = HydroParams(), HydroParams.from_string(text + "[mesh]\nnx=48\n[other]\nflag=false\n")
+    a.setup(cm)
+    assert bytes(a.raw) == bytes(b.raw)
+    # a missing file: ParseError() = -1, an empty map, defaults everywhere (the reference never checks it)
+    missing = ConfigMap("/nonexistent/file.ini")
+    assert missing.ParseError() == -1 and missing.getFloat("hydro", "gamma0", 1.4) == float(np.float32(1.4))
+
+
+def test_profile_switch_is_off_by_default_and_cheap():
+    import ctypes as C
+
+    L = _lib.lib()
+    n, d = C.c_ulonglong(), C.c_int()
+    assert L.e2d_profile_stats(C.byref(n), C.byref(d)) == 0
+    L.e2d_profile_push(b"x")
+    L.e2d_profile_pop()
+    n2 = C.c_ulonglong()
+    L.e2d_profile_stats(C.byref(n2), C.byref(d))
+    assert n2.value == n.value and d.value == 0
+
+
+def test_compat_headers_compile_a_reference_style_host_program(tmp_path):
+    """A host written against the reference's headers (same includes, names and constructor arguments as src/main.cpp)
+    compiles and links against the library through include/euler2d_compat — no GPU is needed to build it."""
+    import subprocess
+
+    src = tmp_path / "host.cpp"
+    src.write_text('''
+#include "kokkos_shared.h"
+#include "HydroBaseFunctor.h"
+#include "ComputeRadialProfileFunctor.h"
+#include "HydroParams.h"
+#include "HydroRun.h"
+#include "real_type.h"
+#include "Timer.h"
+int main(int argc, char * argv[])
+{
+  using device = Kokkos::Device<Kokkos::DefaultExecutionSpace, Kokkos::DefaultExecutionSpace::memory_space>;
+  using real_t = euler2d::real_t;
+  Kokkos::initialize(argc, argv);
+  Timer total_timer;
+  ConfigMap configMap(argc > 1 ? argv[1] : "none.ini");
+  euler2d::HydroParams params = euler2d::HydroParams();
+  params.setup(configMap);
+  if (argc > 2)
+  { // only with a GPU
+    euler2d::HydroRun<device> * hydro = new euler2d::HydroRun<device>(params, configMap);
+    real_t dt = hydro->compute_dt(0);
+    hydro->make_boundaries(hydro->U);
+    Kokkos::Profiling::pushRegion("main_loop");
+    hydro->godunov_unsplit(0, dt);
+    Kokkos::Profiling::popRegion();
+    if (params.problemType == euler2d::PROBLEM_BLAST and params.blast_total_energy_inside > 0)
+      euler2d::ComputeRadialProfileFunctor<device>::apply(params, hydro->U);
+    delete hydro;
+  }
+  Kokkos::finalize();
+  return params.nx == 256 ? 0 : 1;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.join(ROOT, "euler2d_kokkos_b200")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I" + os.path.join(ROOT, "include", "euler2d_compat"), "-o",
+                           str(exe), str(src), "-L" + libdir, "-leuler2d_b200", "-Wl,-rpath," + libdir])
+    ini = tmp_path / "d.ini"
+    from euler2d_kokkos_b200.decks import deck_text
+
+    ini.write_text(deck_text("implode"))
+    assert subprocess.run([str(exe), str(ini)], capture_output=True).returncode == 0
