@@ -923,11 +923,11 @@ extern "C"
     hs.dt = h->dt_last;
     hs.nStep = h->nStep;
     hs.done = !(h->t < p.tEnd && h->nStep < max_steps);
+    hs.solo_T[h->nStep & 3] = h->t; // solo: the first step of the call reads ring slot nStep & 3
     E2D_CUDA(cudaMemcpyAsync(h->d_state, h->h_state, sizeof(SlabState), cudaMemcpyHostToDevice, st));
     {
       const double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
-      // solo: the first step has parity 0 and reads solo_acc[0]
-      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, solo ? &h->d_state->solo_acc[0] : &h->d_state->invdt_acc, st));
+      E2D_CUDA(launch_reduce_invdt(p, h->g, cur, solo ? &h->d_state->solo_acc[h->nStep & 3] : &h->d_state->invdt_acc, st));
     }
 
     SlabStepArgs sa;
@@ -1017,7 +1017,6 @@ extern "C"
       double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
       E2D_CUDA(launch_make_boundaries(p, h->g, cur, faces, nullptr, st));
     }
-    long issued = 0; // steps issued by this call: solo parity
     while (!finished)
     {
       long todo = max_steps - n_host;
@@ -1030,11 +1029,10 @@ extern "C"
         double *  out = which == 0 ? h->U2 : h->U;
         if (solo)
         {
-          so.parity = (int)(issued & 1);
-          ++issued;
+          so.step = n_host;
           if (h->timing)
             E2D_CUDA(cudaEventRecord(h->ev_step[2 * k], st));
-          E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, nullptr, &h->d_state->solo_acc[1 - so.parity], nullptr, st,
+          E2D_CUDA(launch_fused_step(p, h->g, in, out, 0.0, nullptr, &h->d_state->solo_acc[(n_host + 1) & 3], nullptr, st,
                                      nullptr, nullptr, 2, 0, pdl, &so));
           if (h->timing)
             E2D_CUDA(cudaEventRecord(h->ev_step[2 * k + 1], st));

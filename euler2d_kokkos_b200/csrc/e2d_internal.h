@@ -65,22 +65,25 @@ struct SlabState
   int                done;
   int                pending; // dt of an opened step not yet added to t
   int                error;   // a wait for a peer timed out
-  // single-GPU loop folded into the step kernel (SoloLoop): invDt accumulators by step parity, arrival counter
-  unsigned long long solo_acc[2];
-  unsigned int       solo_cnt;
+  // single-GPU loop folded into the step kernel (SoloLoop): rings indexed by (step & 3) — the time at which a step
+  // starts and the invDt maximum of the state it reads.  Step n reads slot n, accumulates the next maximum into slot
+  // n+1, and its first block writes T[n+1] and clears acc[n+2]: no slot is read and written in the same launch.
+  unsigned long long solo_acc[4];
+  double             solo_T[4];
 };
 
 // Single-GPU device-resident loop with ONE launch per step: the step kernel itself opens the step (every block
 // derives dt = cfl / invDt and the tEnd clamp from device memory: src/HydroRun.h:246, src/main.cpp:100,131-134),
-// pushes the boundary fill of the state it has just produced into that array's ghost cells (what make_boundaries
-// would do at the start of the next step, e2d_bc.cuh), and its last block closes the step (t += dt, nStep++, dt
-// history: main.cpp:142-143).
+// its first block does the bookkeeping of main.cpp:142-143 on the way in (t += dt, nStep++, dt history — all blocks
+// derive the same dt, so nothing has to be elected or fenced at the end of the kernel), and every block pushes the
+// boundary fill of the rows it has produced into the output array's ghost cells (what make_boundaries would do at
+// the start of the next step, e2d_bc.cuh).
 struct SoloLoop
 {
   SlabState * st = nullptr;
   double      cfl = 0.0, tEnd = 0.0;
   int         max_steps = 0;
-  int         parity = 0; // the step reads solo_acc[parity], accumulates the next invDt into solo_acc[1 - parity]
+  int         step = 0; // nStep of the state this launch reads: ring slot step & 3
   double *    dt_hist = nullptr;
   long        hist_cap = 0;
   int         bc_xmin = 0, bc_xmax = 0, bc_ymin = 0, bc_ymax = 0;

@@ -596,20 +596,49 @@ publish_to_peers(const MarchArgs & a, const FusedLink & link)
 }
 
 // Epilogue of the single-GPU loop instantiation (SoloLoop, e2d_internal.h).  Out of line for the same reason.
-//  1. Boundary push: every ghost cell whose SOURCE cell (e2d_bc.cuh: bc_map) this block has just produced is written
+//     Boundary push: every ghost cell whose SOURCE cell (e2d_bc.cuh: bc_map) this block has just produced is written
 //     now, into the output array — the fill HydroRun::make_boundaries would do at the start of the next step
 //     (src/HydroRun.h:296, :390-399), same composed index maps, same signs, bit for bit.  Only blocks that hold one of
 //     the columns {2, 3, nx, nx+1} or rows {2, 3, ny, ny+1} have anything to do.
-//  2. The last block to arrive closes the step: t += dt, nStep++, dt history, loop condition (main.cpp:100,142-143),
-//     and clears the invDt accumulator the NEXT-but-one step will fill.
 // dt of the step a SoloLoop launch performs, from the device-resident scalars (HydroRun.h:246, main.cpp:131-134)
 __device__ __forceinline__ double
 solo_dt(const SoloLoop & solo, double t)
 {
-  const double invDt = __longlong_as_double((long long)solo.st->solo_acc[solo.parity]);
+  const double invDt = __longlong_as_double((long long)solo.st->solo_acc[solo.step & 3]);
   double       dt = solo.cfl / invDt;
   if (t + dt > solo.tEnd)
     dt = solo.tEnd - t;
+  return dt;
+}
+
+// Opens the step of a SoloLoop launch: every thread derives the same dt from the same device-resident scalars
+// (HydroRun.h:246, main.cpp:100,131-134), which no block of THIS launch writes (rings, see SlabState); one thread of
+// the grid does the bookkeeping of main.cpp:142-143 on the way in.  Returns -1 once the loop is over.  Out of line so
+// that none of this competes for the marching loop's registers.
+__device__ __noinline__ double
+solo_open_step(const SoloLoop & solo)
+{
+  SlabState *  st = solo.st;
+  const int    k = solo.step & 3;
+  const double t = st->solo_T[k];
+  const bool   over = !(t < solo.tEnd && solo.step < solo.max_steps); // main.cpp:100
+  const double dt = over ? -1.0 : solo_dt(solo, t);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+  {
+    st->solo_T[(k + 1) & 3] = over ? t : t + dt;
+    st->solo_acc[(k + 2) & 3] = 0ull; // the accumulator of the next launch
+    if (!over)
+    {
+      if (solo.dt_hist && solo.step < solo.hist_cap)
+        solo.dt_hist[solo.step] = dt;
+      st->t = t + dt;
+      st->dt = dt;
+      st->nStep = solo.step + 1;
+      st->done = !(t + dt < solo.tEnd && solo.step + 1 < solo.max_steps);
+    }
+    else
+      st->solo_acc[(k + 1) & 3] = st->solo_acc[k]; // nothing changes any more: carry the state's invDt along
+  }
   return dt;
 }
 
@@ -679,27 +708,6 @@ solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
       }
     }
   }
-  __threadfence(); // this block's atomicMax (and ghost cells) before its arrival count
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    SlabState * st = solo.st;
-    if (atomicAdd(&st->solo_cnt, 1u) == gridDim.x * gridDim.y - 1)
-    {
-      st->solo_cnt = 0;
-      __threadfence();
-      const int    n = st->nStep;
-      const double dt = solo_dt(solo, st->t); // the value every block derived at the start of this launch
-      if (solo.dt_hist && n < solo.hist_cap)
-        solo.dt_hist[n] = dt;
-      const double t = st->t + dt; // main.cpp:142-143
-      st->t = t;
-      st->dt = dt;
-      st->nStep = n + 1;
-      st->done = !(t < solo.tEnd && n + 1 < solo.max_steps); // main.cpp:100
-      st->solo_acc[solo.parity] = 0ull; // consumed by every block of this step; refilled by the next step
-    }
-  }
 }
 
 // LOOP: 0 = one step, dt from the arguments;  1 = multi-GPU slab loop (publishes halo rows + invDt partial to the
@@ -715,13 +723,10 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
     return;
   double dt = a.d_dt ? *a.d_dt : a.dt;
   if (LOOP == 2)
-  { // open the step: every thread derives the same dt from the same device-resident scalars (HydroRun.h:246,
-    // main.cpp:100,131-134); they were written by the last block of the previous launch
-    const SlabState * st = solo.st;
-    const double      t = st->t;
-    if (!(t < solo.tEnd && st->nStep < solo.max_steps))
+  {
+    dt = solo_open_step(solo);
+    if (dt < 0.0) // the loop is over (dt is positive otherwise: cfl / invDt or tEnd - t with t < tEnd)
       return;
-    dt = solo_dt(solo, t);
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MarchSmem<kBX> &                  sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
@@ -1347,6 +1352,11 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
   long       best_cost = -1;
   int        best_rows = ny;
   const int  max_seg = ny < 4096 ? ny : 4096;
+  static const int min_rows = [] { // development switch: shortest segment considered
+    const char * e = std::getenv("E2D_MIN_SEG_ROWS");
+    const int    v = e ? std::atoi(e) : 2;
+    return v > 0 ? v : 2;
+  }();
   for (int nseg = 1; nseg <= max_seg; ++nseg)
   {
     const int  rows = (ny + nseg - 1) / nseg;
@@ -1359,7 +1369,7 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
       best_cost = cost;
       best_rows = rows;
     }
-    if (rows <= 2)
+    if (rows <= min_rows)
       break;
   }
   return best_rows < 1 ? 1 : best_rows;

@@ -190,6 +190,8 @@ def test_upload_download_layouts():
 
 
 def test_save_vtk_matches_reference_format(tmp_path):
+    """Layout of the file and the 6-significant-digit values (the stream's default precision).  The byte-for-byte
+    comparison with files written by the reference program itself is in test_gpu_refmain.py."""
     hp, op = both_params("implode", mesh__nx=16, mesh__ny=8, output__outputDir=str(tmp_path),
                          output__outputPrefix="vt")
     with HydroRun(hp) as hydro:
@@ -246,7 +248,7 @@ def test_large_grid_against_oracle(deck, nx, ny, steps):
     assert_bitwise(U[INNER], U_ref[INNER], f"{deck} {nx}x{ny}")
 
 
-def test_full_size_8192_properties():
+def test_full_size_8192_fused_loop_equals_unfused_host_driven_pipeline():
     """configs[2]: four_quadrant 8192^2.  Too big for the oracle in seconds, so check what must hold at any
     size: (1) the fused device-resident run equals the unfused implementation-0 pipeline driven from the host,
     bit for bit (two independent code paths, the second one checked against the oracle above), (2) the fused
