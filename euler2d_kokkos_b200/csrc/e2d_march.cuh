@@ -89,6 +89,16 @@ struct alignas(16) Pair
   double a, b;
 };
 
+// E2D_BULK_FETCH = 1 (experiment, profiles/r2p_bulk_fetch_ab.txt): the next row of conservative states is fetched by
+// ONE elected thread per block with four bulk asynchronous copies (cp.async.bulk, one 1 KB run per variable plane)
+// that complete on an mbarrier, instead of four 8-byte cp.async (LDGSTS) per thread.  A bulk copy lands contiguous
+// bytes, so the U ring becomes planar (UB) and four slots deep: the slot overwritten by the copy of row r+3 was last
+// read in phase B(r-1), which every thread has left when it passes the barrier of row r.
+#ifndef E2D_BULK_FETCH
+#  define E2D_BULK_FETCH 0
+#endif
+#define E2D_BULK (E2D_BULK_FETCH && E2D_LEAN_DEVICE)
+
 template <int BX>
 struct MarchSmem
 {
@@ -98,6 +108,10 @@ struct MarchSmem
   Pair   XMAX[2][2][BX];
   Pair   YMAX[2][2][BX];
   Pair   FX[2][2][BX];
+#if E2D_BULK_FETCH
+  alignas(16) double             UB[4][4][BX]; // planar U ring of the bulk-fetch variant (row & 3)
+  alignas(8) unsigned long long mbar[4];      // one transaction barrier per UB slot
+#endif
 };
 
 // PACKED = false: the same storage read as four planes double[4][BX] with 64-bit accesses (the strict kernel, whose
@@ -250,6 +264,64 @@ struct MarchThread
 #endif
   }
 
+#if E2D_BULK
+  // ---- bulk-fetch variant (strict arithmetic only) ----
+  __device__ static unsigned
+  smem_u32(const void * p)
+  {
+    return (unsigned)__cvta_generic_to_shared(p);
+  }
+  // row j of this block's BX columns -> UB[j & 3], by the calling (elected) thread: four bulk copies, one barrier
+  __device__ void
+  bulk_fetch_row(const MarchArgs & a, MarchSmem<BX> & sm, int j_src, int j) const
+  { // j: the row the loop believes it fetches (ring slot, barrier phase); j_src: the same, clamped to the array
+    const int      i0 = i - t; // first column of the block
+    int            nvalid = a.isize - i0;
+    nvalid = nvalid < BX ? nvalid : BX;
+    const unsigned bytes = (unsigned)nvalid * 8u;
+    const unsigned bar = smem_u32(&sm.mbar[j & 3]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
+    const double * src = a.Uin + (j_src * a.isize + i0);
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(&sm.UB[j & 3][v][0])),
+                   "l"(src + v * plane), "r"(bytes), "r"(bar)
+                   : "memory");
+  }
+  // wait until the bulk copy of row j has landed; rows are fetched in order starting with row j0 + 1
+  __device__ void
+  bulk_wait_row(MarchSmem<BX> & sm, int j) const
+  {
+    const unsigned bar = smem_u32(&sm.mbar[j & 3]);
+    const unsigned parity = (unsigned)(((j - (j0 + 1)) >> 2) & 1);
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+  }
+  __device__ static void
+  ldb4(const double (&row)[4][BX], int t, double v[4])
+  {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      v[k] = row[k][t];
+  }
+  __device__ static void
+  stb4(double (&row)[4][BX], int t, const double v[4])
+  {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      row[k][t] = v[k];
+  }
+#endif
+
   // conservative -> primitive of one cell of a fetched row, into ring slot `slot`
   E2D_HD void
   convert_into(const MarchArgs & a, MarchSmem<BX> & sm, const double u[4], int slot) const
@@ -303,10 +375,36 @@ struct MarchThread
     convert_into(a, sm, u, (j0 - 2) % 3);
     load_row(a, j0 - 1, u);
     convert_into(a, sm, u, (j0 - 1) % 3);
-    st4<PACK>(sm.U[(j0 - 1) % 3], t, u);
+#if E2D_BULK
+    const bool bulk = (MATH == 0);
+    if (bulk)
+      stb4(sm.UB[(j0 - 1) & 3], t, u);
+    else
+#endif
+      st4<PACK>(sm.U[(j0 - 1) % 3], t, u);
     load_row(a, j0, u);
     convert_into(a, sm, u, j0 % 3);
-    st4<PACK>(sm.U[j0 % 3], t, u);
+#if E2D_BULK
+    if (bulk)
+    {
+      stb4(sm.UB[j0 & 3], t, u);
+      // columns past the end of the array are never touched by a bulk copy: give them a valid state in the other slots
+      if (i >= a.isize)
+      {
+        stb4(sm.UB[(j0 + 1) & 3], t, u);
+        stb4(sm.UB[(j0 + 2) & 3], t, u);
+      }
+      if (t == 0)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mbar[k])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+    }
+    else
+#endif
+      st4<PACK>(sm.U[j0 % 3], t, u);
     st4<PACK>(sm.YMAX[(j0 - 2) & 1], t, u); // any valid state: the south face of row j0-1 is solved but unused
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -317,6 +415,18 @@ struct MarchThread
     }
     st4<PACK>(sm.FX[(j0 - 1) & 1], t, fyP); // zeros: read (and unused) by the first phase B
     // row j0+1, read as "row r+2" by the first phase B (r = j0-1)
+#if E2D_BULK
+    if (bulk)
+    { // by the elected thread, once the initialised barriers are visible to everybody
+      __syncthreads(); // (uniform: every thread of an active block gets here)
+      if (t == 0)
+      {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulk_fetch_row(a, sm, j0 + 1 < a.jsize ? j0 + 1 : a.jsize - 1, j0 + 1);
+      }
+      return true;
+    }
+#endif
     prefetch_row(a, sm, (j0 + 1 < a.jsize) ? j0 + 1 : a.jsize - 1, (j0 + 1) % 3);
     return true;
   }
@@ -482,6 +592,22 @@ struct MarchThread
   {
     const int sS = (m3 == 0) ? 2 : m3 - 1;
     double    xl[4], yl[4], fxE[4], uC[4], uP[4], fx[4], fy[4], un[4], qP[4], ryP = 0.0, cflv;
+#if E2D_BULK
+    if (MATH == 0)
+    {
+      bulk_wait_row(sm, r + 2); // row r+2, in flight since the previous phase B
+      ld4<PACK>(sm.XMAX[r & 1], tm, xl);
+      ld4<PACK>(sm.YMAX[(r - 1) & 1], t, yl);
+      ld4<PACK>(sm.FX[r & 1], tp, fxE);
+      ldb4(sm.UB[r & 3], t, uC);
+      ldb4(sm.UB[(r + 2) & 3], t, uP);
+      // row r+3 -> slot (r+3) & 3 = (r-1) & 3, last read (as uC) in phase B(r-1): every thread has passed barrier r since
+      if (t == 0)
+        bulk_fetch_row(a, sm, (r + 3 < a.jsize) ? r + 3 : a.jsize - 1, r + 3);
+    }
+    else
+#endif
+    {
     wait_prefetch(); // row r+2, in flight since phase A
     ld4<PACK>(sm.XMAX[r & 1], tm, xl);
     ld4<PACK>(sm.YMAX[(r - 1) & 1], t, yl);
@@ -491,6 +617,7 @@ struct MarchThread
     // row r+3 (clamped: the last fetches of the topmost segment are harmless repeats) -> the U ring slot of row r,
     // just read; it is consumed by phase B(r+1), a whole B and A phase from here (own column only: no hazard)
     prefetch_row(a, sm, (r + 3 < a.jsize) ? r + 3 : a.jsize - 1, m3);
+    }
     if (MATH == 1)
       compute_B_fast(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv);
     else
