@@ -1412,7 +1412,10 @@ extern "C"
                              cudaMemcpyDeviceToDevice, st));
     E2D_CUDA(launch_loop_begin_step(h->d_loop, p.cfl, 1e300, st));
     E2D_CUDA(launch_fused_step(p, h->g, h->U, h->U2, 0.0, &h->d_loop->dt, nullptr, nullptr, st));
-    // ghosts of the output: the reference's out array carries the input's filled ghosts (HydroRun.h:302)
+    // Ghost cells of the result: filled from the NEW interior (what the next make_boundaries would produce), so that
+    // the array handed back is self-consistent.  This differs from the reference's godunov_unsplit, whose out array
+    // keeps the INPUT's filled ghosts (deep_copy, HydroRun.h:302) — e2d_godunov_unsplit reproduces that; this
+    // convenience entry point has no counterpart in the reference.
     E2D_CUDA(launch_make_boundaries(p, h->g, h->U2, faces_for(h), nullptr, st));
     E2D_CUDA(cudaMemcpyAsync(U_host_out, h->U2, bytes, cudaMemcpyDeviceToHost, st));
     E2D_CUDA(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
@@ -1637,6 +1640,10 @@ extern "C"
     double * A = h ? array_of(h, which) : nullptr;
     if (!A)
       return fail(E2D_ERR_INVALID, "bad argument");
+    if (!h->whole)
+      return fail(E2D_ERR_UNSUPPORTED, "saveData on a y-slab handle: every rank would write its piece under the same file "
+                                       "name; gather the interior (e2d_download / PeerSlabRun.gather_interior) and write it "
+                                       "from one rank");
     if (h->p.vtkAppended)
       return e2d_save_vtk_appended(h, which, iStep);
     cudaSetDevice(h->device); // the handle may be driven from a thread whose current device differs
@@ -1781,6 +1788,8 @@ extern "C"
     double * A = h ? array_of(h, which) : nullptr;
     if (!A)
       return fail(E2D_ERR_INVALID, "bad argument");
+    if (!h->whole)
+      return fail(E2D_ERR_UNSUPPORTED, "saveData on a y-slab handle: gather the interior and write it from one rank");
     cudaSetDevice(h->device);
     const e2d_params & p = h->p;
     const int          nx = p.nx, ny = h->g.ny;

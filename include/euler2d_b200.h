@@ -315,7 +315,9 @@ int      e2d_get_params(e2d_handle * h, e2d_params * out);
 /* End-to-end entry for callers whose state lives in HOST memory (bench.py's e2e leg):
  * H2D of U_host_in (SoA, whole slab incl. ghosts) -> make_boundaries -> compute_dt -> one
  * godunov step -> D2H into U_host_out.  *dt_out receives the dt used.  Pinned host buffers make the
- * copies asynchronous; pageable ones work too. */
+ * copies asynchronous; pageable ones work too.  The ghost cells of the result are filled from the NEW interior (a
+ * self-consistent array); the reference's godunov_unsplit leaves the input's ghosts there (HydroRun.h:302), which
+ * e2d_godunov_unsplit reproduces — this convenience entry point has no counterpart in the reference. */
 int e2d_step_host(e2d_handle * h, const double * U_host_in, double * U_host_out, double * dt_out);
 
 /* The same step for host-resident state, STREAMED: rows go host -> device in chunks of `chunk_rows` (<= 0: ny/32),
@@ -332,7 +334,10 @@ int e2d_step_host_streamed(e2d_handle * h, const double * U_host_in, double * U_
                            double * dt_used, double * dt_next);
 
 /* HydroRun::saveData -> saveVTK (src/HydroRun.h:486-609): ascii .vti, ghosts stripped,
- * <outputDir>/<outputPrefix>_<%07d iStep>.vti, default ostream precision (6 significant digits). */
+ * <outputDir>/<outputPrefix>_<%07d iStep>.vti, default ostream precision (6 significant digits): byte-identical to
+ * the reference program's files (tests/test_gpu_refmain.py).  Whole-domain handles only: on a y-slab handle both VTK
+ * writers return E2D_ERR_UNSUPPORTED (every rank would write its piece under the same name) — gather the interior on
+ * one rank instead (e2d_save_raw writes a slab's own rows and is allowed). */
 int e2d_save_vtk(e2d_handle * h, int which, int iStep);
 
 /* Fast output — same file name, names (rho, E, mx, my: src/HydroParams.cpp:17), extents,

@@ -553,3 +553,28 @@ def test_compute_dt_cache_after_fused_step_is_exact_and_invalidated():
         hydro.device_ptr(HydroRun.U)
         W = hydro.download(HydroRun.U if (n + 1) % 2 == 0 else HydroRun.U2)
         assert hydro.compute_dt((n + 1) % 2) == op.cfl / oracle.compute_invdt(op, W)
+
+
+def test_save_vtk_refuses_slab_handles(tmp_path):
+    """every rank of a slab run would write its piece under the same name: refused with a status code"""
+    from euler2d_kokkos_b200 import Slab
+
+    hp, _ = both_params("implode", mesh__nx=32, mesh__ny=32, output__outputDir=str(tmp_path), run__nOutput=-1)
+    with HydroRun(hp, slab=Slab(0, 2, 16, 0)) as h:
+        for fn in (e2d.lib().e2d_save_vtk, e2d.lib().e2d_save_vtk_appended):
+            assert fn(h._h, 0, 0) == 5  # E2D_ERR_UNSUPPORTED
+    assert not list(tmp_path.iterdir())
+
+
+def test_tall_grid_beyond_gridDim_y_limit():
+    """ny + 4 > 65535 rows: the operator-level kernels spill the row index into gridDim.z"""
+    hp, op = both_params("implode", mesh__nx=8, mesh__ny=70000, mesh__ymax=8750.0, run__nOutput=-1,
+                         other__unfusedKernels="yes")
+    with HydroRun(hp) as hydro:
+        U0 = hydro.download(HydroRun.U)
+        assert_bitwise(U0, oracle.init_slab(op), "init of a 70004-row slab")
+        n, t, dts = host_loop(hydro, hp, 2)
+        U = hydro.download(HydroRun.U)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 2)
+    assert_bitwise(np.array(dts), dts_ref, "dt")
+    assert_bitwise(U[INNER], U_ref[INNER], "tall grid, literal kernel sequence")
