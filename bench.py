@@ -115,7 +115,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------ reference arm
 REF_MAX_TIMED_STEPS = 20  # 8192^2 takes ~1 s per step on 16 cores: W + K steps of it stay within a few minutes
 REF_MAX_WARMUP = 2
-CPU_BASELINE_STEPS, CPU_BASELINE_WARMUP = 8, 1  # the `cpu_baseline` of our own line: the same deck, fewer steps
+CPU_BASELINE_STEPS, CPU_BASELINE_WARMUP = 10, 2  # the `cpu_baseline` of our own line: the same deck, fewer steps
 
 
 def run_reference_sample(nx: int, ny: int, steps: int, warmup: int, threads: int | None = None):
