@@ -1017,33 +1017,11 @@ extern "C"
       double * cur = (h->nStep % 2 == 0) ? h->U : h->U2;
       E2D_CUDA(launch_make_boundaries(p, h->g, cur, faces, nullptr, st));
     }
-    // Grids of less than one wave of blocks: a persistent cooperative launch per batch (k_fused_steps) instead of one
-    // launch per step — unless per-step kernel timers are on, or E2D_NO_PERSISTENT is set (development switch).
-    static const bool persistent_off = std::getenv("E2D_NO_PERSISTENT") != nullptr;
-    bool              persistent = solo && !h->timing && !persistent_off;
     while (!finished)
     {
       long todo = max_steps - n_host;
       if (todo > batch)
         todo = batch;
-      if (persistent)
-      {
-        so.step = n_host;
-        double *          cur = (n_host % 2 == 0) ? h->U : h->U2;
-        double *          other = (n_host % 2 == 0) ? h->U2 : h->U;
-        const cudaError_t e = launch_fused_steps_persistent(p, h->g, cur, other, (int)todo, so, st);
-        if (e == cudaErrorNotSupported)
-        {
-          cudaGetLastError();
-          persistent = false; // too many blocks to be resident at once: step by step from here on
-        }
-        else
-        {
-          E2D_CUDA(e);
-          n_host += (int)todo;
-          todo = 0;
-        }
-      }
       for (long k = 0; k < todo; ++k, ++n_host)
       {
         const int which = n_host % 2; // 0: U -> U2

@@ -165,11 +165,6 @@ cudaError_t launch_fused_step(const e2d_params & p, const Geom & g, const double
                               int j_first = 2, int j_last = 0 /* <= 0: all rows; else rows [j_first, j_last) */,
                               bool pdl = false /* see launch_slab_boundaries */,
                               const SoloLoop * solo = nullptr /* single-GPU loop: dt, invDt, done come from solo->st */);
-// Persistent single-GPU loop for grids of less than one wave of blocks: one cooperative launch, up to nsteps steps, a
-// grid barrier between them.  Ucur is the array step solo.step reads.  cudaErrorNotSupported: the grid does not fit
-// (or the solver has no persistent instantiation) — launch step by step instead.
-cudaError_t launch_fused_steps_persistent(const e2d_params & p, const Geom & g, double * Ucur, double * Uother, int nsteps,
-                                          const SoloLoop & solo, cudaStream_t st);
 int         device_sm_count(); // multiprocessors of the current device (cached per device)
 // refined reciprocal of the strict division sequence for denominator d (device-evaluated once per value, cached;
 // synchronises on a miss — e2d_create warms it for dx, dy so that no launch inside a loop ever misses)

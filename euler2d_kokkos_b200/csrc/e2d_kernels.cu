@@ -4,7 +4,6 @@
 // reference's FMA-free x86 build).  Data layout: SoA planes, off = i + isize*(j + jsize*var);
 // threadIdx.x always walks i, so every global access of a warp is a contiguous 256-byte run.
 #include <atomic>
-#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
@@ -645,7 +644,7 @@ solo_open_step(const SoloLoop & solo)
 
 template <int BX>
 __device__ __noinline__ void
-solo_epilogue(const MarchArgs & a, const SoloLoop & solo, double * __restrict__ Uout)
+solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
 {
   int        j0, j1;
   const bool active = block_rows<BX, 2>(a, j0, j1);
@@ -685,8 +684,8 @@ solo_epilogue(const MarchArgs & a, const SoloLoop & solo, double * __restrict__ 
           continue;
 #pragma unroll
         for (int v = 0; v < 4; ++v)
-          Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
-            bc_value(Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+          a.Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
+            bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
       }
     }
     if (row_src)
@@ -704,8 +703,8 @@ solo_epilogue(const MarchArgs & a, const SoloLoop & solo, double * __restrict__ 
           continue;
 #pragma unroll
         for (int v = 0; v < 4; ++v)
-          Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
-            bc_value(Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+          a.Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
+            bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
       }
     }
   }
@@ -758,48 +757,7 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
   if (LOOP == 1)
     publish_to_peers<kBX>(a, link);
   if (LOOP == 2)
-    solo_epilogue<kBX>(a, solo, a.Uout);
-}
-
-// ------------------------------------------------------------------------------------------
-// Persistent small-grid loop: ONE cooperative launch runs up to `nsteps` steps, with a grid-wide barrier between them.
-// For grids of less than one wave of blocks a step is a chain of latencies (SoloLoop prologue, three rows of global
-// loads, a handful of row-phases, block maximum, boundary push) plus a kernel boundary; keeping the blocks alive
-// removes the boundary and the launch, and keeps the instruction cache warm.  Same arithmetic, same rings, same
-// boundary push as k_fused_step<.., 2, ..>: bit-identical.  The arrays swap roles from step to step (MarchThread::flip).
-// ------------------------------------------------------------------------------------------
-template <int SOLVER, int MATH, int TYP>
-__global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
-k_fused_steps(const __grid_constant__ MarchArgs a, const __grid_constant__ SoloLoop solo, int nsteps)
-{
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  MarchSmem<kBX> &                              sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
-  MarchThread<kBX, SOLVER, true, MATH, TYP, true> th;
-  SoloLoop                                      so = solo;
-  for (int s = 0; s < nsteps; ++s, ++so.step)
-  {
-    const double dt = solo_open_step(so); // the same value in every thread of the grid
-    if (dt < 0.0)
-      break; // the loop is over: uniform over the grid, nobody is left waiting at the barrier
-    th.flip = s & 1;
-    const bool active = th.init(a, sm, threadIdx.x, blockIdx.x, blockIdx.y, dt);
-    if (active)
-    {
-      __syncthreads();
-      for (int r = th.j0 - 1; r <= th.j1; ++r)
-      {
-        th.phaseA(a, sm, r);
-        __syncthreads();
-        th.phaseB(a, sm, r);
-      }
-      th.finish(a);
-      block_max_to_global(th.invdt, &so.st->solo_acc[(so.step + 1) & 3]);
-    }
-    solo_epilogue<kBX>(a, so, th.out_array(a));
-    grid.sync(); // every row, ghost cell and invDt partial of this step is visible before anyone starts the next
-  }
+    solo_epilogue<kBX>(a, solo);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1559,77 +1517,6 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     launch_err = launch_mode<2, 0, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   count_launch();
   return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
-}
-
-// Persistent loop (k_fused_steps): usable when the whole grid of blocks is resident at once.  Returns
-// cudaErrorNotSupported when it is not (the caller then launches step by step).
-namespace
-{
-template <int SOL, int MATH, int TYP>
-cudaError_t
-launch_persistent_instance(const dim3 & grid, size_t smem, cudaStream_t st, MarchArgs & a, SoloLoop & so, int nsteps)
-{
-  static std::atomic<unsigned long long> configured{ 0 };
-  static std::atomic<int>                blocks_per_sm[64] = {};
-  auto                                   kernel = k_fused_steps<SOL, MATH, TYP>;
-  if (cudaError_t e = configure_once(kernel, smem, configured))
-    return e;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  int per_sm = blocks_per_sm[dev & 63].load(std::memory_order_relaxed);
-  if (per_sm <= 0)
-  {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBX, smem) != cudaSuccess || per_sm <= 0)
-      return cudaErrorNotSupported;
-    blocks_per_sm[dev & 63].store(per_sm, std::memory_order_relaxed);
-  }
-  if ((long)grid.x * grid.y > (long)per_sm * device_sm_count())
-    return cudaErrorNotSupported;
-  void * args[3] = { (void *)&a, (void *)&so, (void *)&nsteps };
-  return cudaLaunchCooperativeKernel((const void *)kernel, grid, dim3(kBX), args, smem, st);
-}
-} // namespace
-
-cudaError_t
-launch_fused_steps_persistent(const e2d_params & p, const Geom & g, double * Ucur, double * Uother, int nsteps,
-                              const SoloLoop & solo, cudaStream_t st)
-{
-  MarchArgs a;
-  a.Uin = Ucur; // the array step `solo.step` reads; the roles swap from step to step inside the kernel
-  a.Uout = Uother;
-  a.isize = g.isize;
-  a.jsize = g.jsize;
-  a.s = make_settings(p);
-  a.c = make_step_consts(a.s);
-  a.dt = 0.0;
-  a.d_dt = nullptr;
-  a.invdt_bits = nullptr; // per step: &st->solo_acc[(step + 1) & 3]
-  const int  sol = solver_for(p);
-  const bool fastm = p.arithmetic == E2D_ARITH_FAST && sol == E2D_RIEMANN_HLLC;
-  a.rdx_y = fastm ? 1.0 / a.s.dx : refined_reciprocal(a.s.dx);
-  a.rdy_y = fastm ? 1.0 / a.s.dy : refined_reciprocal(a.s.dy);
-  const int nbx = (g.nx + (kBX - 4) - 1) / (kBX - 4);
-  a.seg_rows = choose_seg_rows(nbx, g.ny, march_min_blocks(fastm ? 1 : 0));
-  const int    nseg = (g.ny + a.seg_rows - 1) / a.seg_rows;
-  const dim3   grid((unsigned)nbx, (unsigned)nseg, 1);
-  const size_t smem = sizeof(MarchSmem<kBX>);
-  const int    typ = !a.c.limited ? 0 : (p.dx == p.dy ? 1 : 2);
-  SoloLoop     so = solo;
-  cudaError_t  e;
-  if (sol != E2D_RIEMANN_HLLC)
-    return cudaErrorNotSupported; // the opt-in solvers keep the step-by-step loop
-  if (fastm)
-    e = typ == 1 ? launch_persistent_instance<2, 1, 1>(grid, smem, st, a, so, nsteps)
-                 : launch_persistent_instance<2, 1, 0>(grid, smem, st, a, so, nsteps);
-  else if (typ == 1)
-    e = launch_persistent_instance<2, 0, 1>(grid, smem, st, a, so, nsteps);
-  else if (typ == 2)
-    e = launch_persistent_instance<2, 0, 2>(grid, smem, st, a, so, nsteps);
-  else
-    e = launch_persistent_instance<2, 0, 0>(grid, smem, st, a, so, nsteps);
-  if (e == cudaSuccess)
-    count_launch();
-  return e;
 }
 
 cudaError_t

@@ -179,10 +179,7 @@ st4(Pair (&row)[2][BX], int t, const double v[4])
 // shocked_bubble deck: 0.445f/445 and 0.089f/89 differ in the last bits);  0: nothing — slope_type and dx == dy are
 // tested at run time, which costs the strict kernel ~40 issue slots per row (predicated multiplies, selects against
 // zero slopes, two DSETPs).
-// PERSIST: the block lives for several steps (persistent small-grid loop, k_fused_steps): the roles of the two arrays
-// of MarchArgs swap from step to step (`flip`), so the array pointers become per-thread values instead of kernel
-// arguments.  Only that instantiation pays for them.
-template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0, int TYP = 0, bool PERSIST = false>
+template <int BX, int SOLVER, bool FUSE_DT, int MATH = 0, int TYP = 0>
 struct MarchThread
 {
 #ifndef E2D_STRICT_PACK
@@ -207,18 +204,6 @@ struct MarchThread
   double pend[4];          // U(r-1) + Fx(i, r-1)
   double unD[4];           // updated state of the row completed by the previous phase B (CFL integrand deferred)
   double invdt;
-  int    flip = 0; // PERSIST: odd steps of a persistent launch read a.Uout and write a.Uin
-
-  E2D_HD const double *
-  in_array(const MarchArgs & a) const
-  {
-    return (PERSIST && flip) ? a.Uout : a.Uin;
-  }
-  E2D_HD double *
-  out_array(const MarchArgs & a) const
-  {
-    return (PERSIST && flip) ? const_cast<double *>(a.Uin) : a.Uout;
-  }
 
   // dx, dy with their reciprocals for the CFL integrand: kernel arguments (constant bank), no registers.  Strict: the
   // refined reciprocal of the division sequence (MarchArgs::rdx_y, computed once on the device); fast: 1.0 / dx.
@@ -243,7 +228,7 @@ struct MarchThread
   load_row(const MarchArgs & a, int j, double u[4]) const
   {
     // 32-bit in-plane offset (isize*jsize < 2^31 is checked at the ABI); the plane stride is block-uniform
-    const double * p = in_array(a) + (j * a.isize + ic);
+    const double * p = a.Uin + (j * a.isize + ic);
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
       u[v] = p[v * plane];
@@ -254,7 +239,7 @@ struct MarchThread
   E2D_HD void
   prefetch_row(const MarchArgs & a, MarchSmem<BX> & sm, int j, int slot) const
   {
-    const double * p = in_array(a) + (j * a.isize + ic);
+    const double * p = a.Uin + (j * a.isize + ic);
 #if E2D_LEAN_DEVICE
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
@@ -296,7 +281,7 @@ struct MarchThread
     const unsigned bytes = (unsigned)nvalid * 8u;
     const unsigned bar = smem_u32(&sm.mbar[j & 3]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
-    const double * src = in_array(a) + (j_src * a.isize + i0);
+    const double * src = a.Uin + (j_src * a.isize + i0);
 #pragma unroll
     for (int v = 0; v < 4; ++v)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -655,7 +640,7 @@ struct MarchThread
     if (store && r >= j0 + 1)
     {
       const int jr = r - 1;
-      double *  po = out_array(a) + (jr * a.isize + i);
+      double *  po = a.Uout + (jr * a.isize + i);
       E2D_UNROLL
       for (int v = 0; v < 4; ++v)
         po[v * plane] = un[v];
