@@ -341,16 +341,20 @@ def baseline_configs(dev, rank, world):
     return out
 
 
+KERNEL_SOURCES = ("e2d_kernels.cu", "e2d_march.cuh", "e2d_lean.cuh", "e2d_fast.cuh", "e2d_math.cuh", "e2d_bc.cuh",
+                  "e2d_internal.h", "Makefile")
+
+
 def csrc_sha():
-    """sha256 over the CUDA sources the kernels are built from: profiles/roofline_traffic.json carries the value it was
-    captured at, so a stale ncu capture is visible in the bench line (`traffic_stale`)."""
-    import glob
+    """sha256 over the sources the step kernels are built from (kernels, device headers, build flags — not the host-side
+    C ABI): profiles/roofline_traffic.json carries the value it was captured at, so a stale ncu capture is visible in
+    the bench line (`traffic_stale`)."""
     import hashlib
 
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "euler2d_kokkos_b200", "csrc", "*.cu*"))):
-        h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
+    for name in KERNEL_SOURCES:
+        h.update(name.encode())
+        h.update(open(os.path.join(ROOT, "euler2d_kokkos_b200", "csrc", name), "rb").read())
     return h.hexdigest()[:16]
 
 

@@ -439,6 +439,12 @@ extern "C"
     if (p->problemType == E2D_PROBLEM_BLAST && p->blast_total_energy_inside > 0 &&
         (jsize_loc != p->jsize || j_off != 0))
       return fail(E2D_ERR_UNSUPPORTED, "energy-renormalised blast init needs the whole domain on one device");
+    // Sedov (blast with total_energy_inside): the energy inside the disc depends on a count over the WHOLE grid
+    // (src/HydroRunFunctors.h:1445-1463); a slab cannot know it from its own rows.  Handles do it with
+    // e2d_blast_inside_count / e2d_blast_renormalise; this stateless entry point refuses.
+    if (p->problemType == E2D_PROBLEM_BLAST && p->blast_total_energy_inside > 0 && (jsize_loc != p->jsize || j_off != 0))
+      return fail(E2D_ERR_UNSUPPORTED, "e2d_k_init_problem: the energy-renormalised blast init needs the whole domain; on "
+                                       "slabs use e2d_create + e2d_blast_inside_count / e2d_blast_renormalise");
     E2D_CUDA(launch_init_problem(*p, make_geom(*p, jsize_loc, j_off), U, (cudaStream_t)stream));
     return E2D_OK;
   }

@@ -371,3 +371,10 @@ def test_sedov_energy_renormalised_init():
     d = dev(np.zeros((4, op.jsize, op.isize)))
     ck(L().e2d_k_init_problem(C.byref(hp.raw), ptr(d), op.jsize, 0, None))
     assert_bitwise(host(d), oracle.init_slab(op), "sedov init")
+
+
+def test_sedov_init_of_a_slab_is_refused_by_the_stateless_entry_point():
+    """the disc energy needs a count over the whole grid: handles do it (e2d_blast_*), e2d_k_init_problem cannot"""
+    hp, op = both_params("sedov_blast_2d", mesh__nx=64, mesh__ny=64)
+    d = dev(np.zeros((4, 20, op.isize)))
+    assert L().e2d_k_init_problem(C.byref(hp.raw), ptr(d), 20, 13, None) == 5  # E2D_ERR_UNSUPPORTED
