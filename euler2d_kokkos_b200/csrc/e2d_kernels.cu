@@ -24,6 +24,9 @@ namespace
 #ifndef E2D_BX
 #  define E2D_BX 128
 #endif
+#ifndef E2D_PUBLISH_FENCE_ALL
+#  define E2D_PUBLISH_FENCE_ALL 1 // every thread fences before the elections of publish_to_peers (0: the electing thread only)
+#endif
 #ifndef E2D_STRICT_MIN_BLOCKS
 #  define E2D_STRICT_MIN_BLOCKS (384 / E2D_BX)
 #endif
@@ -562,6 +565,7 @@ publish_to_peers(const MarchArgs & a, const FusedLink & link)
   // last block of the grid copies the finished invDt partial into every rank's slot and raises the invDt flags.
   // (only the edge blocks have peer stores to drain at system scope; for the others the device-scope fence orders
   //  their atomicMax before their arrival count, which is all the last block's read needs)
+#if E2D_PUBLISH_FENCE_ALL
   if (lo || hi)
     __threadfence_system();
   else
@@ -569,6 +573,17 @@ publish_to_peers(const MarchArgs & a, const FusedLink & link)
   __syncthreads();
   if (threadIdx.x == 0)
   {
+#else
+  // One fence by the electing thread, behind the block barrier: the barrier orders every thread's stores before it and
+  // fences are cumulative (the idiom of cooperative groups' grid barrier) — three warps less waiting on MEMBAR per block
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    if (lo || hi)
+      __threadfence_system();
+    else
+      __threadfence();
+#endif
     if (lo && atomicAdd(&link.cnt[0], 1u) == link.n_lo - 1)
     {
       link.cnt[0] = 0;

@@ -107,3 +107,16 @@ def test_partition_and_ownership():
     assert (p0.lower, p0.faces, p2.upper, p2.faces) == (2, FACES_X, 0, FACES_X)
     with pytest.raises(ValueError):
         slab_geometry(hp, 0, 16)
+
+
+def test_half_periodic_y_is_refused_for_slabs():
+    """only one of the two y faces periodic: no rank pair could close the wrap; whole domains may have it"""
+    import euler2d_kokkos_b200 as e2d
+    from euler2d_kokkos_b200.decks import deck_text
+    from euler2d_kokkos_b200.distributed import slab_geometry
+
+    hp = e2d.HydroParams.from_string(deck_text("implode", mesh__nx=32, mesh__ny=32, mesh__boundary_type_ymin=3,
+                                               mesh__boundary_type_ymax=1))
+    assert slab_geometry(hp, 0, 1).faces == e2d.FACES_ALL
+    with pytest.raises(ValueError, match="periodic"):
+        slab_geometry(hp, 0, 2)
