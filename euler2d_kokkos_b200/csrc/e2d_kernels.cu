@@ -24,9 +24,6 @@ namespace
 #ifndef E2D_BX
 #  define E2D_BX 128
 #endif
-#ifndef E2D_PUBLISH_FENCE_ALL
-#  define E2D_PUBLISH_FENCE_ALL 1 // every thread fences before the elections of publish_to_peers (0: the electing thread only)
-#endif
 #ifndef E2D_STRICT_MIN_BLOCKS
 #  define E2D_STRICT_MIN_BLOCKS (384 / E2D_BX)
 #endif
@@ -565,7 +562,6 @@ publish_to_peers(const MarchArgs & a, const FusedLink & link)
   // last block of the grid copies the finished invDt partial into every rank's slot and raises the invDt flags.
   // (only the edge blocks have peer stores to drain at system scope; for the others the device-scope fence orders
   //  their atomicMax before their arrival count, which is all the last block's read needs)
-#if E2D_PUBLISH_FENCE_ALL
   if (lo || hi)
     __threadfence_system();
   else
@@ -573,17 +569,6 @@ publish_to_peers(const MarchArgs & a, const FusedLink & link)
   __syncthreads();
   if (threadIdx.x == 0)
   {
-#else
-  // One fence by the electing thread, behind the block barrier: the barrier orders every thread's stores before it and
-  // fences are cumulative (the idiom of cooperative groups' grid barrier) — three warps less waiting on MEMBAR per block
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    if (lo || hi)
-      __threadfence_system();
-    else
-      __threadfence();
-#endif
     if (lo && atomicAdd(&link.cnt[0], 1u) == link.n_lo - 1)
     {
       link.cnt[0] = 0;
@@ -686,40 +671,84 @@ solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
     const bool   col_src = (I0 <= 3) || (I1 > nx); // holds a column of {2, 3, nx, nx+1}
     const bool   row_src = (j0 <= 3) || (j1 > ny); // holds a row of {2, 3, ny, ny+1}
     if (col_src)
-    { // x-ghost columns of the rows [j0, j1)
+    { // x-ghost columns of the rows [j0, j1): a long segment gives every thread several cells; their loads are issued
+      // together, four cells at a time, before the first store (loads and stores go through the same pointer, so the
+      // compiler would otherwise serialise one L2 round trip per cell — ~10 us at the tail of the border blocks of a
+      // 249-row segment)
       const int n = 4 * (j1 - j0);
-      for (int k = threadIdx.x; k < n; k += BX)
+      for (int k0 = threadIdx.x; k0 < n; k0 += 4 * BX)
       {
-        const int gsel = k & 3, j = j0 + (k >> 2);
-        const int i = gsel < 2 ? gsel : nx + gsel;
-        int       i0, jj0;
-        bool      in_x, in_y, flip_u, flip_v;
-        bc_map(g, bc, i, j, i0, jj0, in_x, in_y, flip_u, flip_v);
-        if (i0 < I0 || i0 >= I1)
-          continue;
+        double val[4][4];
+        size_t dst[4];
+        bool   take[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          a.Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
-            bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+        for (int b = 0; b < 4; ++b)
+        {
+          const int k = k0 + b * BX;
+          take[b] = k < n;
+          const int kk = take[b] ? k : k0;
+          const int gsel = kk & 3, j = j0 + (kk >> 2);
+          const int i = gsel < 2 ? gsel : nx + gsel;
+          int       i0, jj0;
+          bool      in_x, in_y, flip_u, flip_v;
+          bc_map(g, bc, i, j, i0, jj0, in_x, in_y, flip_u, flip_v);
+          take[b] = take[b] && i0 >= I0 && i0 < I1;
+          if (!take[b])
+            i0 = I0; // a cell of this block: the load stays valid, the value is dropped
+          dst[b] = (size_t)i + (size_t)a.isize * j;
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            val[b][v] = bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (take[b])
+          {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              a.Uout[dst[b] + v * plane] = val[b][v];
+          }
       }
     }
     if (row_src)
-    { // y-ghost rows: this block's own columns and the four x-ghost columns (corners)
+    { // y-ghost rows: this block's own columns and the four x-ghost columns (corners); loads batched like above
       const int own = I1 - I0, ncols = own + 4, n = 4 * ncols;
-      for (int k = threadIdx.x; k < n; k += BX)
+      for (int k0 = threadIdx.x; k0 < n; k0 += 4 * BX)
       {
-        const int gsel = k / ncols, c = k - gsel * ncols;
-        const int j = gsel < 2 ? gsel : ny + gsel;
-        const int i = c < own ? I0 + c : ((c - own) < 2 ? (c - own) : nx + (c - own));
-        int       i0, jj0;
-        bool      in_x, in_y, flip_u, flip_v;
-        bc_map(g, bc, i, j, i0, jj0, in_x, in_y, flip_u, flip_v);
-        if (i0 < I0 || i0 >= I1 || jj0 < j0 || jj0 >= j1)
-          continue;
+        double val[4][4];
+        size_t dst[4];
+        bool   take[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          a.Uout[(size_t)i + (size_t)a.isize * j + v * plane] =
-            bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+        for (int b = 0; b < 4; ++b)
+        {
+          const int k = k0 + b * BX;
+          take[b] = k < n;
+          const int kk = take[b] ? k : k0;
+          const int gsel = kk / ncols, c = kk - gsel * ncols;
+          const int j = gsel < 2 ? gsel : ny + gsel;
+          const int i = c < own ? I0 + c : ((c - own) < 2 ? (c - own) : nx + (c - own));
+          int       i0, jj0;
+          bool      in_x, in_y, flip_u, flip_v;
+          bc_map(g, bc, i, j, i0, jj0, in_x, in_y, flip_u, flip_v);
+          take[b] = take[b] && i0 >= I0 && i0 < I1 && jj0 >= j0 && jj0 < j1;
+          if (!take[b])
+          { // a cell of this block: the load stays valid, the value is dropped
+            i0 = I0;
+            jj0 = j0;
+          }
+          dst[b] = (size_t)i + (size_t)a.isize * j;
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            val[b][v] = bc_value(a.Uout, (size_t)i0 + (size_t)a.isize * jj0 + v * plane, v, in_x, in_y, flip_u, flip_v);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (take[b])
+          {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              a.Uout[dst[b] + v * plane] = val[b][v];
+          }
       }
     }
   }
