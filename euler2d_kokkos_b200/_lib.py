@@ -124,6 +124,7 @@ SIGNATURES = {
     "e2d_get_params": (C.c_int, [_vp, _pp]),
     "e2d_step_host": (C.c_int, [_vp, _vp, _vp, _dp]),
     "e2d_step_host_streamed": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, _dp, _dp]),
+    "e2d_march_host": (C.c_int, [_vp, _vp, _vp, C.c_long, C.c_int, _dp, _dp]),
     "e2d_save_vtk": (C.c_int, [_vp, C.c_int, C.c_int]),
     "e2d_save_vtk_appended": (C.c_int, [_vp, C.c_int, C.c_int]),
     "e2d_save_raw": (C.c_int, [_vp, C.c_int, C.c_char_p]),

@@ -1640,6 +1640,162 @@ extern "C"
     return E2D_OK;
   }
 
+  // A time march whose state lives in HOST memory, the steps PIPELINED.  e2d_step_host_streamed overlaps the two copy
+  // directions and the kernel inside one step but returns between steps, so every step pays the head of its pipeline
+  // (nothing can come back before the first rows have arrived and been advanced) and its tail.  Here the host -> device
+  // stream never stops: the rows of step s+1 follow the rows of step s as soon as (a) the way back of the same rows in
+  // step s has landed in the host buffer they are read from and (b) the kernels of step s no longer read the device
+  // rows they overwrite.  dt never visits the host: the CFL maximum rides on the chunk kernels, a one-thread kernel forms
+  // dt = cfl / invDt between the steps (HydroRun.h:246).  tEnd is not looked at: the caller chooses nsteps.
+  int
+  e2d_march_host(e2d_handle * h, double * buf_a, double * buf_b, long nsteps, int chunk_rows, double * dts, double * t_io)
+  {
+    if (!h || !buf_a || !buf_b || nsteps < 0)
+      return fail(E2D_ERR_INVALID, "bad argument");
+    if (!h->whole)
+      return fail(E2D_ERR_UNSUPPORTED, "e2d_march_host needs the whole domain on one device (slabs: e2d_step_host_streamed "
+                                       "per step, ghost rows exchanged by the caller)");
+    E2D_REFUSE_PENDING(h);
+    const e2d_params & p = h->p;
+    if (p.boundary_type_ymin == E2D_BC_PERIODIC || p.boundary_type_ymax == E2D_BC_PERIODIC)
+      return fail(E2D_ERR_UNSUPPORTED, "e2d_march_host: a periodic y direction makes the first rows of a step depend on the "
+                                       "last rows of the step before; use e2d_step_host_streamed per step");
+    cudaSetDevice(h->device);
+    const Geom & g = h->g;
+    cudaStream_t st = h->stream;
+    const int    isize = g.isize, jsize = g.jsize, ny = g.ny;
+    const size_t plane = (size_t)isize * jsize;
+    const int    faces = faces_for(h);
+    if (nsteps == 0)
+      return E2D_OK;
+    if (!h->s_in)
+    {
+      E2D_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+      E2D_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    }
+    // uniform chunks of interior rows (>= 16 rows: every chunk holds the source rows of the faces next to it)
+    if (chunk_rows <= 0)
+      chunk_rows = (ny + 63) / 64;
+    if (chunk_rows < 16)
+      chunk_rows = 16;
+    std::vector<int> jb;
+    for (int j = 2; j < jsize - 2; j += chunk_rows)
+      jb.push_back(j);
+    if (jb.size() > 1 && jsize - 2 - jb.back() < 16)
+      jb.pop_back(); // a remainder too short to stand alone joins the chunk before it
+    jb.push_back(jsize - 2);
+    const int nchunk = (int)jb.size() - 1;
+    // events: [parity][kind][chunk], kind 0 = rows landed on the device, 1 = chunk advanced, 2 = rows landed on the host
+    while ((int)h->ev_pool.size() < 6 * nchunk + 4)
+    {
+      cudaEvent_t e;
+      E2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_pool.push_back(e);
+    }
+    auto ev = [&](int parity, int kind, int k) { return h->ev_pool[(size_t)((parity * 3 + kind) * nchunk + k)]; };
+    cudaEvent_t ev_start = h->ev_pool[6 * nchunk];
+    auto copy_rows = [&](double * dst, const double * src, int jlo, int jhi, cudaMemcpyKind kind, cudaStream_t s) {
+      const size_t o = (size_t)jlo * isize;
+      return cudaMemcpy2DAsync(dst + o, plane * sizeof(double), src + o, plane * sizeof(double),
+                               (size_t)(jhi - jlo) * isize * sizeof(double), 4, kind, s);
+    };
+    // dt of every step, on the device until the end
+    double * d_dts = nullptr;
+    E2D_CUDA(cudaMalloc(&d_dts, sizeof(double) * (size_t)nsteps));
+    int rc = E2D_OK;
+#define E2D_MARCH(call)                       \
+  {                                           \
+    cudaError_t e_ = (call);                  \
+    if (e_ != cudaSuccess && rc == E2D_OK)    \
+      rc = fail_cuda(e_, #call);              \
+  }
+    h->h_loop->t = t_io ? *t_io : 0.0;
+    h->h_loop->dt = 0.0;
+    h->h_loop->nStep = 0;
+    h->h_loop->done = 0;
+    h->h_loop->invdt_cur = 0;
+    h->h_loop->invdt_next = 0;
+    E2D_MARCH(cudaMemcpyAsync(h->d_loop, h->h_loop, sizeof(LoopState), cudaMemcpyHostToDevice, st));
+    E2D_MARCH(cudaEventRecord(ev_start, st));
+    E2D_MARCH(cudaStreamWaitEvent(h->s_in, ev_start, 0));
+    E2D_MARCH(cudaStreamWaitEvent(h->s_out, ev_start, 0));
+
+    for (long s = 0; s < nsteps && rc == E2D_OK; ++s)
+    {
+      const int      par = (int)(s & 1), prev = 1 - par;
+      const double * in = par == 0 ? buf_a : buf_b;
+      double *       out = par == 0 ? buf_b : buf_a;
+      // ---- host -> device (interior rows only: the physical ghost cells are refilled on the device)
+      for (int k = 0; k < nchunk; ++k)
+      {
+        if (s > 0)
+        {
+          E2D_MARCH(cudaStreamWaitEvent(h->s_in, ev(prev, 2, k), 0));                                   // (a)
+          E2D_MARCH(cudaStreamWaitEvent(h->s_in, ev(prev, 1, k + 1 < nchunk ? k + 1 : nchunk - 1), 0)); // (b)
+        }
+        E2D_MARCH(copy_rows(h->U, in, jb[k], jb[k + 1], cudaMemcpyHostToDevice, h->s_in));
+        E2D_MARCH(cudaEventRecord(ev(par, 0, k), h->s_in));
+      }
+      if (s == 0)
+      { // the first dt needs the whole state: main.cpp:87,128
+        E2D_MARCH(cudaStreamWaitEvent(st, ev(par, 0, nchunk - 1), 0));
+        E2D_MARCH(launch_reduce_invdt(p, g, h->U, &h->d_loop->invdt_cur, st));
+      }
+      E2D_MARCH(launch_loop_begin_step(h->d_loop, p.cfl, 1e300, st));
+      // ---- fill, advance, device -> host
+      auto advance = [&](int m) {
+        const int ja = jb[m], jz = jb[m + 1];
+        if (s > 0)
+          E2D_MARCH(cudaStreamWaitEvent(st, ev(prev, 2, m), 0)); // the previous result's rows have left U2
+        E2D_MARCH(launch_fused_step(p, g, h->U, h->U2, 0.0, &h->d_loop->dt, &h->d_loop->invdt_next, nullptr, st, nullptr,
+                                    nullptr, ja, jz));
+        E2D_MARCH(launch_bc_x_rows(p, g, h->U2, faces, ja, jz, st)); // ghost columns of the result
+        E2D_MARCH(cudaEventRecord(ev(par, 1, m), st));
+        E2D_MARCH(cudaStreamWaitEvent(h->s_out, ev(par, 1, m), 0));
+        E2D_MARCH(copy_rows(out, h->U2, ja, jz, cudaMemcpyDeviceToHost, h->s_out));
+        E2D_MARCH(cudaEventRecord(ev(par, 2, m), h->s_out));
+      };
+      for (int k = 0; k < nchunk; ++k)
+      {
+        E2D_MARCH(cudaStreamWaitEvent(st, ev(par, 0, k), 0));
+        E2D_MARCH(launch_bc_x_rows(p, g, h->U, faces, jb[k], jb[k + 1], st));
+        if (k == 0 && (faces & E2D_FACES_YMIN))
+          E2D_MARCH(launch_make_boundaries(p, g, h->U, E2D_FACES_YMIN, nullptr, st));
+        if (k == nchunk - 1 && (faces & E2D_FACES_YMAX))
+          E2D_MARCH(launch_make_boundaries(p, g, h->U, E2D_FACES_YMAX, nullptr, st));
+        if (k >= 1)
+          advance(k - 1);
+        if (k == nchunk - 1)
+          advance(k);
+      }
+      E2D_MARCH(launch_loop_end_step(h->d_loop, 1e300, 2147483647, d_dts, nsteps, st));
+    }
+    // ghost rows of the final state (the interior rows' ghost columns travelled with them)
+    double * last = (nsteps & 1) ? buf_b : buf_a;
+    if (rc == E2D_OK)
+    {
+      cudaEvent_t ev_fin = h->ev_pool[6 * nchunk + 1];
+      E2D_MARCH(launch_make_boundaries(p, g, h->U2, faces & (E2D_FACES_YMIN | E2D_FACES_YMAX), nullptr, st));
+      E2D_MARCH(cudaEventRecord(ev_fin, st));
+      E2D_MARCH(cudaStreamWaitEvent(h->s_out, ev_fin, 0));
+      E2D_MARCH(copy_rows(last, h->U2, 0, 2, cudaMemcpyDeviceToHost, h->s_out));
+      E2D_MARCH(copy_rows(last, h->U2, jsize - 2, jsize, cudaMemcpyDeviceToHost, h->s_out));
+      E2D_MARCH(cudaMemcpyAsync(h->h_loop, h->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, st));
+    }
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->s_out);
+    cudaStreamSynchronize(st);
+    if (rc == E2D_OK && dts)
+      E2D_MARCH(cudaMemcpy(dts, d_dts, sizeof(double) * (size_t)nsteps, cudaMemcpyDeviceToHost));
+    cudaFree(d_dts);
+#undef E2D_MARCH
+    if (rc == E2D_OK && t_io)
+      *t_io = h->h_loop->t;
+    h->loop_primed = false;
+    h->cfl_valid[0] = h->cfl_valid[1] = false;
+    return rc;
+  }
+
   int
   e2d_save_vtk(e2d_handle * h, int which, int iStep)
   {

@@ -252,6 +252,18 @@ class HydroRun:
                                            C.byref(nxt)), "e2d_step_host_streamed")
         return used.value, nxt.value
 
+    def march_host(self, buf_a, buf_b, nsteps: int, chunk_rows: int = 0, t0: float = 0.0):
+        """nsteps steps of a state that lives in host memory, ping-ponging between two (pinned) host buffers, every step
+        streamed through the device and the steps pipelined (e2d_march_host).  buf_a / buf_b: numpy arrays or raw host
+        pointers.  Returns (dts, t); the result is in buf_a for an even nsteps, in buf_b for an odd one."""
+        pa = buf_a if isinstance(buf_a, int) else buf_a.ctypes.data
+        pb = buf_b if isinstance(buf_b, int) else buf_b.ctypes.data
+        dts = np.zeros(max(int(nsteps), 1))
+        t = C.c_double(t0)
+        check(lib().e2d_march_host(self._h, pa, pb, int(nsteps), int(chunk_rows), dts.ctypes.data_as(C.POINTER(C.c_double)),
+                                   C.byref(t)), "e2d_march_host")
+        return dts[: int(nsteps)], t.value
+
     def device_ptr(self, which: int) -> int:
         return lib().e2d_device_ptr(self._h, int(which)) or 0
 

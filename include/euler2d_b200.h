@@ -333,6 +333,20 @@ int e2d_step_host(e2d_handle * h, const double * U_host_in, double * U_host_out,
 int e2d_step_host_streamed(e2d_handle * h, const double * U_host_in, double * U_host_out, double dt_in, int chunk_rows,
                            double * dt_used, double * dt_next);
 
+/* A time march whose state lives in HOST memory (the loop of src/main.cpp:100-143 for a caller that keeps its arrays on
+ * the host): nsteps steps, the state ping-ponging between two host buffers of e2d layout [var][j][i] — step s reads
+ * buf_a and writes buf_b when s is even, the other way round when odd, so the result is in buf_a for an even nsteps
+ * and in buf_b for an odd one.  Every step moves the whole state host -> device and back, chunked by rows like
+ * e2d_step_host_streamed, and the steps are PIPELINED: the upload of step s+1 follows the upload of step s without a
+ * gap, each chunk as soon as the same rows of step s have landed in the host buffer, so both PCIe directions stay
+ * busy across steps (a per-step call pays the head and the tail of its pipeline every time).  dt = cfl / max invDt is
+ * formed on the device between the steps (HydroRun.h:246) and never visits the host; dts (may be NULL) receives the dt of
+ * every step afterwards, *t_io (may be NULL) is advanced by their sum.  params.tEnd is not looked at: the caller chooses
+ * nsteps.  Pinned host buffers are needed for the copies to be asynchronous.  Whole-domain handles without a periodic y
+ * direction only (E2D_ERR_UNSUPPORTED otherwise: use e2d_step_host_streamed).  Results are bit-identical to e2d_run. */
+int e2d_march_host(e2d_handle * h, double * buf_a, double * buf_b, long nsteps, int chunk_rows, double * dts,
+                   double * t_io);
+
 /* HydroRun::saveData -> saveVTK (src/HydroRun.h:486-609): ascii .vti, ghosts stripped,
  * <outputDir>/<outputPrefix>_<%07d iStep>.vti, default ostream precision (6 significant digits): byte-identical to
  * the reference program's files (tests/test_gpu_refmain.py).  Whole-domain handles only: on a y-slab handle both VTK

@@ -578,3 +578,50 @@ def test_tall_grid_beyond_gridDim_y_limit():
     U_ref, dts_ref, n_ref, t_ref = oracle.run(op, 2)
     assert_bitwise(np.array(dts), dts_ref, "dt")
     assert_bitwise(U[INNER], U_ref[INNER], "tall grid, literal kernel sequence")
+
+
+@pytest.mark.parametrize("deck,ov,chunk_rows,nsteps", [
+    ("implode", dict(mesh__nx=96, mesh__ny=200), 16, 7),
+    ("four_quadrant", dict(mesh__nx=130, mesh__ny=257), 40, 10),
+    ("shocked_bubble", dict(mesh__nx=178, mesh__ny=111), 0, 5),
+    ("blast", dict(mesh__nx=64, mesh__ny=96), 500, 4),          # one chunk
+    ("sedov_blast_2d", dict(mesh__nx=64, mesh__ny=64, run__tEnd=1e9), 16, 6),  # (tEnd is not looked at by the march)
+])
+def test_march_host_pipelined_is_bit_identical(deck, ov, chunk_rows, nsteps):
+    """e2d_march_host: the state lives in two pinned host buffers, every step goes through the device chunk by chunk and
+    the steps are pipelined (the upload of step s+1 chases the way back of step s).  Interior, ghost cells of the final
+    state, dt of every step and the time must equal the oracle's bit for bit."""
+    import torch
+
+    hp, op = both_params(deck, run__nOutput=-1, **ov)
+    U_ref, dts_ref, n_ref, t_ref = oracle.run(op, nsteps)
+    with HydroRun(hp) as hydro:
+        n = 4 * hp.jsize * hp.isize
+        a = torch.empty(n, dtype=torch.float64).pin_memory()
+        b = torch.empty(n, dtype=torch.float64).pin_memory()
+        a.numpy()[:] = hydro.download(HydroRun.U).ravel()
+        b.fill_(float("nan"))
+        dts, t = hydro.march_host(a.data_ptr(), b.data_ptr(), nsteps, chunk_rows)
+        res = (a if nsteps % 2 == 0 else b).numpy().reshape(4, hp.jsize, hp.isize)
+    assert t == t_ref
+    assert_bitwise(dts, dts_ref[1:], "dt of every step")
+    assert_bitwise(res[INNER], U_ref[INNER], f"{deck}: interior after {nsteps} pipelined host steps")
+    # ghost cells of the final state = the boundary fill of its own interior
+    full = U_ref.copy()
+    oracle.make_boundaries(op, full)
+    assert_bitwise(res, full, "final state incl. ghost cells")
+
+
+def test_march_host_refuses_what_it_cannot_pipeline():
+    import torch
+
+    from euler2d_kokkos_b200 import Slab
+
+    hp, _ = both_params("implode", mesh__nx=32, mesh__ny=32, run__nOutput=-1, mesh__boundary_type_ymin=3,
+                        mesh__boundary_type_ymax=3)
+    buf = torch.zeros(2 * 4 * 36 * 36, dtype=torch.float64).pin_memory()
+    with HydroRun(hp) as h:
+        assert e2d.lib().e2d_march_host(h._h, buf.data_ptr(), buf.data_ptr() + 4 * 36 * 36 * 8, 2, 0, None, None) == 5
+    hp2, _ = both_params("implode", mesh__nx=32, mesh__ny=32, run__nOutput=-1)
+    with HydroRun(hp2, slab=Slab(0, 2, 16, 0)) as h:
+        assert e2d.lib().e2d_march_host(h._h, buf.data_ptr(), buf.data_ptr() + 4 * 36 * 36 * 8, 2, 0, None, None) == 5
