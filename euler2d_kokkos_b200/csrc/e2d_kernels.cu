@@ -505,16 +505,55 @@ st_release_sys_u64(unsigned long long * p, unsigned long long v)
 // 4 % of the fast kernel's throughput).
 // the rows [j0, j1) and the column a thread of this block owns, recomputed from the block indices: the epilogues take
 // nothing from the marching loop's registers (values kept alive for them cost the loop a spill and three S2Rs)
+// Which column block and row segment a thread block works on.  Blocks are handed to the SMs in the order of their
+// linear index, and the first ones to become resident are the first ones to finish (measured: tools/step_timeline.py):
+//   LOOP == 1 (peers): the two EDGE segments come first, so that the halo rows are on their way (and usually landed)
+//             while the interior is still being computed;
+//   LOOP == 2 (single-GPU loop), E2D_BORDER_FIRST=1 only (experiment, off): every block whose epilogue pushes
+//             boundary cells comes first — the first and last segment, then the first and last column block of the
+//             other segments, then the interior.  Measured (profiles/r3q_border_first_ab.txt): no gain — which of the
+//             blocks sharing an SM finishes first is decided by the SM's warp slots, not by the block index.
+#ifndef E2D_BORDER_FIRST
+#  define E2D_BORDER_FIRST 0
+#endif
+template <int LOOP>
+__device__ __forceinline__ void
+block_place(int & bx, int & seg)
+{
+  bx = blockIdx.x;
+  seg = blockIdx.y;
+  const int nbx = gridDim.x, nseg = gridDim.y;
+  if (LOOP == 1)
+    seg = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? nseg - 1 : (int)blockIdx.y - 1);
+  if (LOOP == 2 && E2D_BORDER_FIRST && nbx >= 3 && nseg >= 3)
+  {
+    int L = blockIdx.y * nbx + blockIdx.x;
+    if (L < 2 * nbx)
+    {
+      seg = L < nbx ? 0 : nseg - 1;
+      bx = L < nbx ? L : L - nbx;
+      return;
+    }
+    L -= 2 * nbx;
+    if (L < 2 * (nseg - 2))
+    {
+      bx = (L & 1) ? nbx - 1 : 0;
+      seg = 1 + (L >> 1);
+      return;
+    }
+    L -= 2 * (nseg - 2);
+    seg = L / (nbx - 2);
+    bx = 1 + (L - seg * (nbx - 2));
+    seg += 1;
+  }
+}
+
 template <int BX, int LOOP>
 __device__ __forceinline__ bool
-block_rows(const MarchArgs & a, int & j0, int & j1)
+block_rows(const MarchArgs & a, int & j0, int & j1, int & bx)
 {
-  int seg = blockIdx.y;
-  if (LOOP == 1)
-  {
-    const int nseg = gridDim.y;
-    seg = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? nseg - 1 : (int)blockIdx.y - 1);
-  }
+  int seg;
+  block_place<LOOP>(bx, seg);
   const int j_end = a.j_last > 0 ? a.j_last : a.jsize - 2;
   j0 = a.j_first + seg * a.seg_rows;
   j1 = j0 + a.seg_rows;
@@ -527,9 +566,9 @@ template <int BX>
 __device__ __noinline__ void
 publish_to_peers(const MarchArgs & a, const FusedLink & link)
 {
-  int        j0, j1;
-  const bool active = block_rows<BX, 1>(a, j0, j1);
-  const int  t = threadIdx.x, i = blockIdx.x * (BX - 4) + t;
+  int        j0, j1, bx;
+  const bool active = block_rows<BX, 1>(a, j0, j1, bx);
+  const int  t = threadIdx.x, i = bx * (BX - 4) + t;
   const bool store = (t >= 2) && (t <= BX - 3) && (i >= 2) && (i <= a.isize - 3);
   const bool lo = active && a.peer_lo && j0 <= 3 && j1 > 2;
   const bool hi = active && a.peer_hi && j0 <= a.jsize - 3 && j1 > a.jsize - 4;
@@ -646,9 +685,8 @@ template <int BX>
 __device__ __noinline__ void
 solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
 {
-  int        j0, j1;
-  const bool active = block_rows<BX, 2>(a, j0, j1);
-  const int  bx = blockIdx.x;
+  int        j0, j1, bx;
+  const bool active = block_rows<BX, 2>(a, j0, j1, bx);
   __syncthreads(); // this block's stores to Uout are visible to all its threads
   if (active)
   {
@@ -754,6 +792,34 @@ solo_epilogue(const MarchArgs & a, const SoloLoop & solo)
   }
 }
 
+// E2D_TIMELINE=1 (development build, tools/step_timeline.py): every block of the single-GPU loop kernel stamps the
+// global nanosecond timer at its milestones into a device buffer that e2d_debug_timeline() copies out — where the time
+// of a small-grid step goes (profiles/r3n_step_timeline.txt).  Compiled out of the product.
+#ifndef E2D_TIMELINE
+#  define E2D_TIMELINE 0
+#endif
+#if E2D_TIMELINE
+constexpr int                 kTimelineBlocks = 1024, kTimelineMarks = 8;
+__device__ unsigned long long g_timeline[4][kTimelineBlocks][kTimelineMarks]; // [step & 3]: the last four steps
+__device__ __forceinline__ unsigned long long
+timeline_now()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void
+timeline_mark(int step, int k, unsigned long long t)
+{
+  const unsigned b = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0 && b < (unsigned)kTimelineBlocks)
+    g_timeline[step & 3][b][k] = t;
+}
+#  define E2D_MARK(k) timeline_mark(solo.step, k, timeline_now())
+#else
+#  define E2D_MARK(k)
+#endif
+
 // LOOP: 0 = one step, dt from the arguments;  1 = multi-GPU slab loop (publishes halo rows + invDt partial to the
 // peers, e2d_slab.cu);  2 = single-GPU loop with one launch per step (SoloLoop: dt, boundary push, bookkeeping).
 template <int SOLVER, bool FUSE_DT, int LOOP, int MATH = 0, int TYP = 0>
@@ -761,8 +827,14 @@ __global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
 k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_done,
              const __grid_constant__ FusedLink link, const __grid_constant__ SoloLoop solo)
 {
+#if E2D_TIMELINE
+  const unsigned long long tl0 = timeline_now();
+#endif
   pdl_wait_for_predecessor(); // (no-ops unless launched with the programmatic-serialization attribute)
   pdl_release_successor();
+#if E2D_TIMELINE
+  const unsigned long long tl1 = timeline_now();
+#endif
   if (d_done && *d_done)
     return;
   double dt = a.d_dt ? *a.d_dt : a.dt;
@@ -772,21 +844,28 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
     if (dt < 0.0) // the loop is over (dt is positive otherwise: cfl / invDt or tEnd - t with t < tEnd)
       return;
   }
+#if E2D_TIMELINE
+  timeline_mark(solo.step, 0, tl0); // (a launch past the end of the loop has returned above and leaves no marks)
+  timeline_mark(solo.step, 1, tl1);
+#endif
+  E2D_MARK(2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MarchSmem<kBX> &                  sm = *reinterpret_cast<MarchSmem<kBX> *>(smem_raw);
   MarchThread<kBX, SOLVER, FUSE_DT, MATH, TYP> th;
-  // blockIdx.y -> row segment: with peers the two EDGE segments come first, so that the halo rows are on their way
-  // (and usually landed) while the interior is still being computed
-  int seg = blockIdx.y;
-  if (LOOP == 1)
+  int bx, seg;
+  block_place<LOOP>(bx, seg);
+  const bool active = th.init(a, sm, threadIdx.x, bx, seg, dt);
+#if E2D_TIMELINE
   {
-    const int nseg = gridDim.y;
-    seg = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1 ? nseg - 1 : (int)blockIdx.y - 1);
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    timeline_mark(solo.step, 7, (unsigned long long)smid | ((unsigned long long)bx << 16) | ((unsigned long long)seg << 32));
   }
-  const bool active = th.init(a, sm, threadIdx.x, blockIdx.x, seg, dt);
+#endif
   if (active)
   {
     __syncthreads();
+    E2D_MARK(3);
 #pragma unroll(MATH == 1 ? kMarchUnrollFast : kMarchUnrollStrict)
     for (int r = th.j0 - 1; r <= th.j1; ++r)
     {
@@ -794,14 +873,17 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
       __syncthreads();
       th.phaseB(a, sm, r);
     }
+    E2D_MARK(4);
     th.finish(a);
     if (FUSE_DT && a.invdt_bits)
       block_max_to_global(th.invdt, a.invdt_bits);
+    E2D_MARK(5);
   }
   if (LOOP == 1)
     publish_to_peers<kBX>(a, link);
   if (LOOP == 2)
     solo_epilogue<kBX>(a, solo);
+  E2D_MARK(6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1562,6 +1644,18 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   count_launch();
   return launch_err != cudaSuccess ? launch_err : cudaGetLastError();
 }
+
+#if E2D_TIMELINE
+} // namespace e2d
+extern "C" int
+e2d_debug_timeline(unsigned long long * out, int nblocks)
+{
+  (void)nblocks; // out: [4][kTimelineBlocks = 1024][kTimelineMarks = 8]
+  return (int)cudaMemcpyFromSymbol(out, e2d::g_timeline, sizeof(e2d::g_timeline));
+}
+namespace e2d
+{
+#endif
 
 cudaError_t
 preload_step_kernels()
