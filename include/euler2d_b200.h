@@ -343,7 +343,9 @@ int e2d_step_host_streamed(e2d_handle * h, const double * U_host_in, double * U_
  * formed on the device between the steps (HydroRun.h:246) and never visits the host; dts (may be NULL) receives the dt of
  * every step afterwards, *t_io (may be NULL) is advanced by their sum.  params.tEnd is not looked at: the caller chooses
  * nsteps.  Pinned host buffers are needed for the copies to be asynchronous.  Whole-domain handles without a periodic y
- * direction only (E2D_ERR_UNSUPPORTED otherwise: use e2d_step_host_streamed).  Results are bit-identical to e2d_run. */
+ * direction only (E2D_ERR_UNSUPPORTED otherwise: use e2d_step_host_streamed).  Results are bit-identical to e2d_run.
+ * The handle's own device arrays are staging space here (as for e2d_step_host*): afterwards they do not hold the
+ * result — e2d_upload it before continuing with the device-resident entry points. */
 int e2d_march_host(e2d_handle * h, double * buf_a, double * buf_b, long nsteps, int chunk_rows, double * dts,
                    double * t_io);
 
