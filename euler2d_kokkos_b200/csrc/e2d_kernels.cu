@@ -1483,6 +1483,12 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
     const int    v = e ? std::atoi(e) : 2;
     return v > 0 ? v : 2;
   }();
+  static const int forced_rows = [] { // development switch: this many rows per segment, whatever the grid
+    const char * e = std::getenv("E2D_SEG_ROWS");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (forced_rows > 0)
+    return forced_rows < ny ? forced_rows : ny;
   for (int nseg = 1; nseg <= max_seg; ++nseg)
   {
     const int  rows = (ny + nseg - 1) / nseg;
