@@ -554,12 +554,7 @@ block_rows(const MarchArgs & a, int & j0, int & j1, int & bx)
 {
   int seg;
   block_place<LOOP>(bx, seg);
-  const int j_end = a.j_last > 0 ? a.j_last : a.jsize - 2;
-  j0 = a.j_first + seg * a.seg_rows;
-  j1 = j0 + a.seg_rows;
-  if (j1 > j_end)
-    j1 = j_end;
-  return j0 < j1;
+  return segment_rows(a, seg, j0, j1);
 }
 
 template <int BX>
@@ -1507,6 +1502,46 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
   return best_rows < 1 ? 1 : best_rows;
 }
 
+// Tapered segments.  Blocks are handed to the SMs in the order of their segment index, an SM shares its issue slots
+// among its resident blocks, and when the queue runs dry every SM finishes what it holds with two, then one block —
+// at 65 % and 43 % of its throughput (tools/step_timeline.py).  With uniform segments that drain costs about half a
+// block's duration per step (3 % at 8192^2 with 155-row segments).  So the segment length follows the work that is
+// left ("guided" scheduling): a block takes 1/guide (1.5) of the fair share of the remaining rows per resident slot,
+// never less than min_rows (48; profiles/r3v_seg_taper_sweep.txt: 1.25-1.75 and 32-48 are all within 0.5 %, 1.0 falls off a
+// cliff on wide grids) — long blocks (few re-traced rows) while there is plenty to do, short ones at the end.  Grids of
+// less than two waves of uniform blocks, and grids that would need more than the table holds, keep uniform segments.
+// Returns the number of segments.  (E2D_SEG_TAPER=0 switches it off, 2 forces it on grids of any size — the parity tests
+// of the table path; E2D_SEG_GUIDE / E2D_SEG_MIN_ROWS tune it: A/B runs.)
+static int
+taper_segments(int nbx, int rows, int blocks_per_sm, int uniform_rows, int uniform_nseg, MarchArgs & a)
+{
+  static const int    enabled = [] { const char * e = std::getenv("E2D_SEG_TAPER"); return e ? std::atoi(e) : 1; }();
+  static const double guide = [] { const char * e = std::getenv("E2D_SEG_GUIDE"); return e ? std::atof(e) : 1.5; }();
+  static const int    min_rows = [] { const char * e = std::getenv("E2D_SEG_MIN_ROWS"); return e ? std::atoi(e) : 48; }();
+  a.seg_tab_n = 0;
+  const int slots = device_sm_count() * blocks_per_sm;
+  if (!enabled || guide < 1.0 || min_rows < 2)
+    return uniform_nseg;
+  if (enabled != 2 && ((long)nbx * uniform_nseg < 2L * slots || uniform_rows <= min_rows)) // 2: tests force it on small grids
+    return uniform_nseg;
+  int n = 0, at = 0;
+  a.seg_tab[0] = 0;
+  while (at < rows)
+  {
+    if (n == MarchArgs::kSegTabMax)
+      return uniform_nseg; // does not fit the table: uniform segments (seg_tab_n stays 0)
+    int len = (int)((double)(rows - at) * nbx / (guide * slots));
+    if (len < min_rows)
+      len = min_rows;
+    if (rows - at - len < min_rows / 2) // no sliver at the end
+      len = rows - at;
+    at += len;
+    a.seg_tab[++n] = at;
+  }
+  a.seg_tab_n = n;
+  return n;
+}
+
 namespace
 {
 // one-time, per device, per instantiation: opt in to the dynamic shared memory the kernel needs
@@ -1599,7 +1634,8 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   // `[other] arithmetic=fast` (e2d_fast.cuh) exists for the HLLC solver, i.e. for everything the reference can run
   const bool fastm = p.arithmetic == E2D_ARITH_FAST && sol == E2D_RIEMANN_HLLC;
   a.seg_rows = choose_seg_rows(nbx, rows, march_min_blocks(fastm ? 1 : 0));
-  const int  nseg = (rows + a.seg_rows - 1) / a.seg_rows;
+  int nseg = (rows + a.seg_rows - 1) / a.seg_rows;
+  nseg = taper_segments(nbx, rows, march_min_blocks(fastm ? 1 : 0), a.seg_rows, nseg, a);
   const dim3 grid((unsigned)nbx, (unsigned)nseg, 1);
   const bool fuse = d_invdt_bits != nullptr;
   FusedLink  lk{};
@@ -1614,8 +1650,16 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     a.peer_lo_jsize = peers->lo_jsize;
     a.peer_hi_jsize = peers->hi_jsize;
     // segments holding interior rows {0,1} / {ny-2, ny-1} (ny >= 2)
-    link->n_lo = (unsigned)nbx * (a.seg_rows == 1 ? 2u : 1u);
-    link->n_hi = (unsigned)nbx * (((g.ny - 2) / a.seg_rows != (g.ny - 1) / a.seg_rows) ? 2u : 1u);
+    auto seg_of = [&](int row) {
+      if (a.seg_tab_n == 0)
+        return row / a.seg_rows;
+      int k = 0;
+      while (k + 1 < a.seg_tab_n && a.seg_tab[k + 1] <= row)
+        ++k;
+      return k;
+    };
+    link->n_lo = (unsigned)nbx * (seg_of(0) != seg_of(1) ? 2u : 1u);
+    link->n_hi = (unsigned)nbx * (seg_of(g.ny - 2) != seg_of(g.ny - 1) ? 2u : 1u);
     link->n_all = (unsigned)nbx * (unsigned)nseg;
     lk = *link;
     mode = 2;

@@ -56,7 +56,13 @@ struct MarchArgs
   const double *       Uin;
   double *             Uout;
   int                  isize, jsize; // slab extent incl. ghosts
-  int                  seg_rows;     // interior rows per block segment
+  int                  seg_rows;     // interior rows per block segment (uniform segments: seg_tab_n == 0)
+  // Tapered segments (launch_fused_step, e2d_kernels.cu): segment k produces the rows [seg_tab[k], seg_tab[k+1]) counted
+  // from j_first, long segments first and ever shorter ones towards the end of the block queue, so that the SMs run
+  // dry together instead of each finishing a long block alone.
+  static constexpr int kSegTabMax = 191;
+  int                  seg_tab_n = 0;
+  int                  seg_tab[kSegTabMax + 1];
   int                  j_first = 2;  // rows [j_first, j_last) are produced (j_last <= 0: jsize - 2); a sub-range lets the
   int                  j_last = 0;   // host-streamed step (e2d_capi.cu) advance chunk by chunk as the rows arrive
   Settings             s;
@@ -98,6 +104,26 @@ struct alignas(16) Pair
 #  define E2D_BULK_FETCH 0
 #endif
 #define E2D_BULK (E2D_BULK_FETCH && E2D_LEAN_DEVICE)
+
+// interior rows [j0, j1) of segment `seg`; false when the segment is empty
+E2D_HD bool
+segment_rows(const MarchArgs & a, int seg, int & j0, int & j1)
+{
+  const int j_end = a.j_last > 0 ? a.j_last : a.jsize - 2;
+  if (a.seg_tab_n > 0)
+  {
+    j0 = a.j_first + a.seg_tab[seg];
+    j1 = a.j_first + a.seg_tab[seg + 1];
+  }
+  else
+  {
+    j0 = a.j_first + seg * a.seg_rows;
+    j1 = j0 + a.seg_rows;
+  }
+  if (j1 > j_end)
+    j1 = j_end;
+  return j0 < j1;
+}
 
 template <int BX>
 struct MarchSmem
@@ -355,12 +381,7 @@ struct MarchThread
     ic = i < a.isize ? i : a.isize - 1;
     store = (t >= 2) && (t <= BX - 3) && (i >= 2) && (i <= a.isize - 3);
     plane = (size_t)a.isize * a.jsize;
-    const int j_end = a.j_last > 0 ? a.j_last : a.jsize - 2;
-    j0 = a.j_first + seg * a.seg_rows;
-    j1 = j0 + a.seg_rows;
-    if (j1 > j_end)
-      j1 = j_end;
-    if (j0 >= j1)
+    if (!segment_rows(a, seg, j0, j1))
       return false;
     dtdx = dt / a.s.dx; // HydroRun.h:290-291
     dtdy = dt / a.s.dy;

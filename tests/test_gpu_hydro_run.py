@@ -625,3 +625,22 @@ def test_march_host_refuses_what_it_cannot_pipeline():
     hp2, _ = both_params("implode", mesh__nx=32, mesh__ny=32, run__nOutput=-1)
     with HydroRun(hp2, slab=Slab(0, 2, 16, 0)) as h:
         assert e2d.lib().e2d_march_host(h._h, buf.data_ptr(), buf.data_ptr() + 4 * 36 * 36 * 8, 2, 0, None, None) == 5
+
+
+# ------------------------------------------------------------------ tapered segments (launch_fused_step)
+@pytest.mark.gpu
+@pytest.mark.parametrize("guide,min_rows", [("1.5", "5"), ("3", "2"), ("2", "17")])
+def test_tapered_segments_are_bit_identical(guide, min_rows):
+    """Large grids are split into segments of decreasing length (taper_segments, e2d_kernels.cu); the switches are read
+    once per process, so the table path is forced onto small decks in a child process: five decks through the
+    device-resident loop, state and dt history bitwise against the oracle (tools/parity_check.py), and the same through
+    two slabs on one device (the halo-publishing instantiation counts its edge blocks from the table)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, E2D_SEG_TAPER="2", E2D_SEG_GUIDE=guide, E2D_SEG_MIN_ROWS=min_rows)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "parity_check.py"), "--slabs"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("state bitwise: True") >= 6, r.stdout

@@ -1,5 +1,6 @@
 """Development aid: bitwise check of the device-resident loop of the library named by E2D_LIB_PATH against the CPU oracle on
-a few even-sized decks (A/B variants whose kernels have stricter alignment needs than the shipped one)."""
+a few even-sized decks (A/B variants whose kernels have stricter alignment needs than the shipped one).
+--slabs: also two y-slabs on this device through the peer-memory loop (tests/test_gpu_hydro_run.py::run_peer_slabs)."""
 import os
 import sys
 import tempfile
@@ -30,4 +31,13 @@ for deck, ov, steps in (("implode", dict(mesh__nx=256, mesh__ny=128), 100), ("fo
     same_dt = np.array_equal(dts, dts_ref[1:])
     print(deck, ov, "state bitwise:", same, "dt bitwise:", same_dt, flush=True)
     ok = ok and same and same_dt
+    if "--slabs" in sys.argv and deck in ("four_quadrant", "shocked_bubble"):
+        sys.path.insert(0, "tests")
+        from test_gpu_hydro_run import run_peer_slabs
+
+        Us, st, dts = run_peer_slabs(hp, 2, steps)
+        same = np.array_equal(Us.view(np.uint64), np.ascontiguousarray(U_ref[:, 2:-2, 2:-2]).view(np.uint64))
+        same_dt = np.array_equal(dts, dts_ref[1:])
+        print(deck, ov, "two slabs: state bitwise:", same, "dt bitwise:", same_dt, flush=True)
+        ok = ok and same and same_dt
 sys.exit(0 if ok else 1)
