@@ -1507,9 +1507,12 @@ choose_seg_rows(int nbx, int ny, int blocks_per_sm)
 // at 65 % and 43 % of its throughput (tools/step_timeline.py).  With uniform segments that drain costs about half a
 // block's duration per step (3 % at 8192^2 with 155-row segments).  So the segment length follows the work that is
 // left ("guided" scheduling): a block takes 1/guide (1.5) of the fair share of the remaining rows per resident slot,
-// never less than min_rows (48; profiles/r3v_seg_taper_sweep.txt: 1.25-1.75 and 32-48 are all within 0.5 %, 1.0 falls off a
-// cliff on wide grids) — long blocks (few re-traced rows) while there is plenty to do, short ones at the end.  Grids of
-// less than two waves of uniform blocks, and grids that would need more than the table holds, keep uniform segments.
+// never less than min_rows (32; profiles/r3v_seg_taper_sweep.txt: 1.25-1.75 and 32-48 are all within 0.5 % on the large
+// grids, 1.0 falls off a cliff on wide ones) — long blocks (few re-traced rows) while there is plenty to do, short ones at
+// the end.  That also pays for a grid of a single wave of uniform blocks (4096^2: +8 %): the blocks that share an SM do
+// not finish together, so a lone wave drains just the same.  Grids whose fair share of rows per resident slot is below
+// 6 minimal segments (3072^2 and smaller: the re-traced rows then cost more than the drain), and grids that would need
+// more segments than the table holds, keep uniform segments.
 // Returns the number of segments.  (E2D_SEG_TAPER=0 switches it off, 2 forces it on grids of any size — the parity tests
 // of the table path; E2D_SEG_GUIDE / E2D_SEG_MIN_ROWS tune it: A/B runs.)
 static int
@@ -1517,12 +1520,16 @@ taper_segments(int nbx, int rows, int blocks_per_sm, int uniform_rows, int unifo
 {
   static const int    enabled = [] { const char * e = std::getenv("E2D_SEG_TAPER"); return e ? std::atoi(e) : 1; }();
   static const double guide = [] { const char * e = std::getenv("E2D_SEG_GUIDE"); return e ? std::atof(e) : 1.5; }();
-  static const int    min_rows = [] { const char * e = std::getenv("E2D_SEG_MIN_ROWS"); return e ? std::atoi(e) : 48; }();
+  static const int    min_rows = [] { const char * e = std::getenv("E2D_SEG_MIN_ROWS"); return e ? std::atoi(e) : 32; }();
   a.seg_tab_n = 0;
   const int slots = device_sm_count() * blocks_per_sm;
   if (!enabled || guide < 1.0 || min_rows < 2)
     return uniform_nseg;
-  if (enabled != 2 && ((long)nbx * uniform_nseg < 2L * slots || uniform_rows <= min_rows)) // 2: tests force it on small grids
+  // worth it once the fair share of rows per resident slot is several minimal segments long — also for a grid of a
+  // single wave of uniform blocks: the blocks sharing an SM do not finish together, so that wave drains just the same
+  static const double fair_min = [] { const char * e = std::getenv("E2D_SEG_TAPER_FAIR"); return e ? std::atof(e) : 6.0; }();
+  (void)uniform_rows;
+  if (enabled != 2 && (double)rows * nbx / slots < fair_min * min_rows) // 2: tests force it on small grids
     return uniform_nseg;
   int n = 0, at = 0;
   a.seg_tab[0] = 0;
