@@ -426,12 +426,21 @@ struct MarchThread
     else
 #endif
       st4<PACK>(sm.U[j0 % 3], t, u);
-    st4<PACK>(sm.YMAX[(j0 - 2) & 1], t, u); // any valid state: the south face of row j0-1 is solved but unused
+    // The first phase B (r = j0-1) solves the south face of row j0-1 and "completes" row j0-2; neither result is used,
+    // but the completed state goes through the deferred CFL integrand of the next phase B, whose guards would send
+    // the whole phase down the plain-operator path if it were not a healthy state (once per segment: measured as
+    // 0.7 row-times).  So: the face's left state is row j0-1's own primitive state (a flux of physical size), and the
+    // pending sum starts from row j0's state instead of zero.
+    {
+      double qb[4];
+      ld4<PACK>(sm.Q[(j0 - 1) % 3], t, qb);
+      st4<PACK>(sm.YMAX[(j0 - 2) & 1], t, qb);
+    }
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
       fyP[v] = 0.0;
-      pend[v] = 0.0;
+      pend[v] = u[v];
       unD[v] = u[v]; // any valid state
     }
     st4<PACK>(sm.FX[(j0 - 1) & 1], t, fyP); // zeros: read (and unused) by the first phase B
