@@ -817,7 +817,11 @@ timeline_mark(int step, int k, unsigned long long t)
 
 // LOOP: 0 = one step, dt from the arguments;  1 = multi-GPU slab loop (publishes halo rows + invDt partial to the
 // peers, e2d_slab.cu);  2 = single-GPU loop with one launch per step (SoloLoop: dt, boundary push, bookkeeping).
-template <int SOLVER, bool FUSE_DT, int LOOP, int MATH = 0, int TYP = 0>
+// PEEL: the march with the first and last row of a segment treated apart (MarchThread::phaseB<1>, <2>: three of a
+// segment's Riemann solves serve nobody).  A kernel of its own, used for SHORT uniform segments only: in the one kernel
+// the two extra phase A bodies cost the long marches 4 % (code size, spills: profiles/r2a_variants.txt, r4m), while a
+// grid of 2- to 64-row segments gains 2-9 %.
+template <int SOLVER, bool FUSE_DT, int LOOP, int MATH = 0, int TYP = 0, bool PEEL = false>
 __global__ void __launch_bounds__(kBX, march_min_blocks(MATH))
 k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_done,
              const __grid_constant__ FusedLink link, const __grid_constant__ SoloLoop solo)
@@ -861,12 +865,31 @@ k_fused_step(const __grid_constant__ MarchArgs a, const int * __restrict__ d_don
   {
     __syncthreads();
     E2D_MARK(3);
-#pragma unroll(MATH == 1 ? kMarchUnrollFast : kMarchUnrollStrict)
-    for (int r = th.j0 - 1; r <= th.j1; ++r)
+    if (PEEL)
     {
-      th.phaseA(a, sm, r);
+      th.phaseA(a, sm, th.j0 - 1);
       __syncthreads();
-      th.phaseB(a, sm, r);
+      th.template phaseB<1>(a, sm, th.j0 - 1);
+#pragma unroll 1
+      for (int r = th.j0; r < th.j1; ++r)
+      {
+        th.phaseA(a, sm, r);
+        __syncthreads();
+        th.template phaseB<0>(a, sm, r);
+      }
+      th.phaseA(a, sm, th.j1);
+      __syncthreads();
+      th.template phaseB<2>(a, sm, th.j1);
+    }
+    else
+    {
+#pragma unroll(MATH == 1 ? kMarchUnrollFast : kMarchUnrollStrict)
+      for (int r = th.j0 - 1; r <= th.j1; ++r)
+      {
+        th.phaseA(a, sm, r);
+        __syncthreads();
+        th.phaseB(a, sm, r);
+      }
     }
     E2D_MARK(4);
     th.finish(a);
@@ -1567,13 +1590,13 @@ configure_once(K kernel, size_t smem, std::atomic<unsigned long long> & done_mas
   return e;
 }
 
-template <int SOL, bool FUSE, int LOOP, int MATH, int TYP>
+template <int SOL, bool FUSE, int LOOP, int MATH, int TYP, bool PEEL = false>
 cudaError_t
 launch_instance(const dim3 & grid, size_t smem, cudaStream_t st, bool pdl, const MarchArgs & a, const int * d_done,
                 const FusedLink & lk, const SoloLoop & so)
 {
   static std::atomic<unsigned long long> configured{ 0 };
-  auto                                   kernel = k_fused_step<SOL, FUSE, LOOP, MATH, TYP>;
+  auto                                   kernel = k_fused_step<SOL, FUSE, LOOP, MATH, TYP, PEEL>;
   if (cudaError_t e = configure_once(kernel, smem, configured))
     return e;
   cudaLaunchConfig_t cfg = {};
@@ -1680,6 +1703,10 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
   }
   // what is known about the deck becomes a template argument of the HLLC strict kernel (MarchThread<.., TYP>)
   const int    typ = !a.c.limited ? 0 : (p.dx == p.dy ? 1 : 2);
+  // the peeled march: single-GPU loop, strict HLLC, short uniform segments (k_fused_step<.., PEEL>); E2D_NO_PEEL=1: A/B runs
+  static const bool no_peel = std::getenv("E2D_NO_PEEL") != nullptr;
+  const bool        peel = mode == 3 && !fastm && sol == E2D_RIEMANN_HLLC && a.seg_tab_n == 0 && a.seg_rows <= 64 && !no_peel &&
+                    !E2D_BULK_FETCH;
   const size_t smem = sizeof(MarchSmem<kBX>);
   cudaError_t  launch_err;
   if (sol == E2D_RIEMANN_APPROX)
@@ -1692,6 +1719,10 @@ launch_fused_step(const e2d_params & p, const Geom & g, const double * Uin, doub
     launch_err = launch_mode<2, 1, 1>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (fastm)
     launch_err = launch_mode<2, 1, 0>(mode, grid, smem, st, pdl, a, d_done, lk, so);
+  else if (peel && typ == 1)
+    launch_err = launch_instance<2, true, 2, 0, 1, true>(grid, smem, st, pdl, a, d_done, lk, so);
+  else if (peel && typ == 2)
+    launch_err = launch_instance<2, true, 2, 0, 2, true>(grid, smem, st, pdl, a, d_done, lk, so);
   else if (typ == 1)
     launch_err = launch_mode<2, 0, 1>(mode, grid, smem, st, pdl, a, d_done, lk, so);
   else if (typ == 2)
@@ -1737,6 +1768,10 @@ preload_step_kernels()
   E2D_PRE(2, 1, 0)
   E2D_PRE(2, 1, 1)
 #undef E2D_PRE
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_fused_step<2, true, 2, 0, 1, true>);
+  if (e == cudaSuccess)
+    e = cudaFuncGetAttributes(&fa, k_fused_step<2, true, 2, 0, 2, true>);
   return e;
 }
 

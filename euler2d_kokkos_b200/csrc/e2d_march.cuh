@@ -444,6 +444,7 @@ struct MarchThread
       unD[v] = u[v]; // any valid state
     }
     st4<PACK>(sm.FX[(j0 - 1) & 1], t, fyP); // zeros: read (and unused) by the first phase B
+    st4<PACK>(sm.FX[j0 & 1], t, fyP);       // zeros: what phase B(j0) reads when the first phase B is the peeled one (phaseB<1>)
     // row j0+1, read as "row r+2" by the first phase B (r = j0-1)
 #if E2D_BULK
     if (bulk)
@@ -507,7 +508,10 @@ struct MarchThread
   // in lock step (e2d_lean.cuh) — the primitives of the fetched row r+2 together with the primitives + CFL
   // integrand of the row completed by the PREVIOUS phase B (deferred by one row so that its long serial chain
   // overlaps other work instead of trailing the update).
-  template <bool LEAN>
+  // PART 2: the last phase B of a segment (r = j1) in the peeled march — the x fluxes of row j1 and the primitives of
+  // row j1+2 belong to the segment above; only the south face is solved, row j1-1 completed and the deferred CFL
+  // integrand evaluated.
+  template <bool LEAN, int PART = 0>
   E2D_HD void
   compute_B(const MarchArgs & a, const double xl[4], const double yl[4], const double fxE[4], const double uP[4],
             double fx[4], double fy[4], double un[4], double qP[4], double & ryP, double & cflv, bool & ok) const
@@ -516,23 +520,26 @@ struct MarchThread
     if (SOLVER == 2)
     {
       // west face of cell (i, r): left = XMAX of (i-1, r), right = XMIN of (i, r) (HydroRunFunctors.h:559-575)
-      hllc_lean<LEAN, true>(s, a.c, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP],
-                      fx[IU], fx[IV], ok);
+      if (PART == 0)
+        hllc_lean<LEAN, true>(s, a.c, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID],
+                              fx[IP], fx[IU], fx[IV], ok);
       // south face of row r: left = YMAX of row r-1, right = YMIN of row r, IU<->IV swapped (:621-640)
       hllc_lean<LEAN, true>(s, a.c, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP],
                       fy[IV], fy[IU], ok);
     }
     else
     {
-      riemann<SOLVER>(s, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP], fx[IU],
-                      fx[IV]);
+      if (PART == 0)
+        riemann<SOLVER>(s, xl[ID], xl[IP], xl[IU], xl[IV], xmin[ID], xmin[IP], xmin[IU], xmin[IV], fx[ID], fx[IP], fx[IU],
+                        fx[IV]);
       riemann<SOLVER>(s, yl[ID], yl[IP], yl[IV], yl[IU], ymin[ID], ymin[IP], ymin[IV], ymin[IU], fy[ID], fy[IP], fy[IV],
                       fy[IU]);
     }
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      fx[v] = fx[v] * dtdx;
+      if (PART == 0)
+        fx[v] = fx[v] * dtdx;
       fy[v] = fy[v] * (SQUARE ? dtdx : dtdy);
     }
     // complete row r-1: UpdateFunctor order (HydroRunFunctors.h:695-713)
@@ -546,7 +553,20 @@ struct MarchThread
       un[v] = x;
     }
     cflv = 0.0;
-    if (FUSE_DT)
+    if (PART == 2)
+    {
+      if (FUSE_DT)
+      {
+        double u1[1][4], q1[1][4];
+        Recip  rd1[1];
+        E2D_UNROLL
+        for (int v = 0; v < 4; ++v)
+          u1[0][v] = unD[v];
+        prim_lean_multi<LEAN, 1>(s, a.c, u1, q1, rd1, ok);
+        cflv = cfl_tail_lean<LEAN>(s, recip_dx(a), recip_dy(a), q1[0], rd1[0], ok);
+      }
+    }
+    else if (FUSE_DT)
     {
       double u2[2][4], q2[2][4];
       Recip  rd2[2];
@@ -617,11 +637,29 @@ struct MarchThread
     fast::prim(s, a.c, uP, qP, ryP);
   }
 
+  // PART 0: a phase B as described at the top of this file — every phase B of the plain march.  The PEELED march (strict
+  // arithmetic, short uniform segments: k_fused_step<.., PEEL>) treats the first and the last row of a segment apart,
+  // because three of the Riemann solves of a segment serve nobody:
+  // PART 1: the first phase B (r = j0-1) — nothing to solve, only the ring is advanced: row r+2 converted, row r+3
+  //         fetched.  Phase B(j0) then "completes" row j0-1 from the start-up values of init (pending sum = row j0's
+  //         state, zero east and south fluxes): a healthy state, discarded like before.
+  // PART 2: the last one (r = j1) — only the south face, the update of row j1-1 and the deferred CFL integrand; nothing
+  //         is fetched or converted any more.
+  template <int PART = 0>
   E2D_HD void
   phaseB(const MarchArgs & a, MarchSmem<BX> & sm, int r)
   {
     const int sS = (m3 == 0) ? 2 : m3 - 1;
     double    xl[4], yl[4], fxE[4], uC[4], uP[4], fx[4], fy[4], un[4], qP[4], ryP = 0.0, cflv;
+    if (PART == 1)
+    {
+      wait_prefetch(); // row r+2, in flight since init
+      ld4<PACK>(sm.U[sS], t, uP);
+      prefetch_row(a, sm, (r + 3 < a.jsize) ? r + 3 : a.jsize - 1, m3);
+      convert_into(a, sm, uP, sS);
+      m3 = (m3 == 2) ? 0 : m3 + 1;
+      return;
+    }
 #if E2D_BULK
     if (MATH == 0)
     {
@@ -637,6 +675,7 @@ struct MarchThread
     }
     else
 #endif
+    if (PART == 0)
     {
     wait_prefetch(); // row r+2, in flight since phase A
     ld4<PACK>(sm.XMAX[r & 1], tm, xl);
@@ -648,19 +687,28 @@ struct MarchThread
     // just read; it is consumed by phase B(r+1), a whole B and A phase from here (own column only: no hazard)
     prefetch_row(a, sm, (r + 3 < a.jsize) ? r + 3 : a.jsize - 1, m3);
     }
+    else
+    {
+      wait_prefetch(); // nothing may stay in flight when the block ends
+      ld4<PACK>(sm.YMAX[(r - 1) & 1], t, yl);
+      ld4<PACK>(sm.FX[r & 1], tp, fxE);
+    }
     if (MATH == 1)
       compute_B_fast(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv);
     else
     {
       bool ok = a.c.lean_ok != 0;
-      compute_B<true>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
+      compute_B<true, PART>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
       if (!ok)
-        compute_B<false>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
+        compute_B<false, PART>(a, xl, yl, fxE, uP, fx, fy, un, qP, ryP, cflv, ok);
     }
 
-    st4<PACK>(sm.FX[(r + 1) & 1], t, fx);
-    st4<PACK>(sm.Q[sS], t, qP); // row r+2 -> primitive ring, slot of row r-1 (last read in A(r))
-    sm.RY[sS][t] = ryP;
+    if (PART == 0)
+    {
+      st4<PACK>(sm.FX[(r + 1) & 1], t, fx);
+      st4<PACK>(sm.Q[sS], t, qP); // row r+2 -> primitive ring, slot of row r-1 (last read in A(r))
+      sm.RY[sS][t] = ryP;
+    }
 
     // the CFL integrand just computed belongs to row r-2 (completed by the previous phase B)
     // invDt = fmax(invDt, v) (HydroRunFunctors.h:72) as compare + select: a NaN v compares false and is dropped like
@@ -679,11 +727,26 @@ struct MarchThread
     E2D_UNROLL
     for (int v = 0; v < 4; ++v)
     {
-      pend[v] = (MATH == 1) ? fast::fmadd(fx[v], dtdx, uC[v]) : uC[v] + fx[v];
-      fyP[v] = fy[v];
+      if (PART == 0)
+      {
+        pend[v] = (MATH == 1) ? fast::fmadd(fx[v], dtdx, uC[v]) : uC[v] + fx[v];
+        fyP[v] = fy[v];
+      }
       unD[v] = un[v];
     }
     m3 = (m3 == 2) ? 0 : m3 + 1;
+  }
+
+  // phase B of row r in the peeled march, whichever part of the segment it is (host emulation of that march)
+  E2D_HD void
+  phaseB_peeled(const MarchArgs & a, MarchSmem<BX> & sm, int r)
+  {
+    if (r == j0 - 1)
+      phaseB<1>(a, sm, r);
+    else if (r == j1)
+      phaseB<2>(a, sm, r);
+    else
+      phaseB<0>(a, sm, r);
   }
 
   // after the last phase B: the CFL integrand of the last completed row (j1-1)

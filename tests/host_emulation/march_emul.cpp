@@ -30,6 +30,14 @@ settings_of(const e2d_params & p)
   return s;
 }
 
+static int g_peel = 0; // emul_set_peel: drive the peeled march (phaseB<1>, <0>..., <2>) instead of the plain one
+
+extern "C" void
+emul_set_peel(int on)
+{
+  g_peel = on;
+}
+
 template <int BX, int SOLVER, int MATH = 0>
 static double
 run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_loc, double dt, int seg_rows)
@@ -69,7 +77,12 @@ run_blocks(const e2d_params & p, const double * Uin, double * Uout, int jsize_lo
           th[t].phaseA(a, *sm, r);
         // __syncthreads()
         for (int t = BX - 1; t >= 0; --t) // reverse order: phase B must not depend on intra-phase ordering
-          th[t].phaseB(a, *sm, r);
+        {
+          if (g_peel && MATH == 0)
+            th[t].phaseB_peeled(a, *sm, r);
+          else
+            th[t].phaseB(a, *sm, r);
+        }
       }
       for (int t = 0; t < BX; ++t)
       {
